@@ -1,0 +1,109 @@
+"""ctypes binding of ``libfreepose_b200.so`` (include/freepose_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, a ``RuntimeError`` is
+raised.  Tensors stay owned by PyTorch; raw ``data_ptr()`` values are borrowed for the call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libfreepose_b200.so"
+
+FP_INPUT_IMAGE_F32, FP_INPUT_IMAGE_BF16, FP_INPUT_PATCHES = 0, 1, 2
+FP_FEATURE_ALL, FP_FEATURE_CLS, FP_FEATURE_REG, FP_FEATURE_PATCH = 0, 1, 2, 3
+FP_EPI_BIAS, FP_EPI_BIAS_GELU, FP_EPI_BIAS_LS_RES, FP_EPI_PATCH_EMBED = 0, 1, 2, 3
+KPAD = 640
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",
+        "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [("depth", C.c_int), ("layers", C.POINTER(VitLayer)), ("patch_w", C.c_void_p),
+                ("patch_b", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p),
+                ("pos_res", C.c_int), ("pos_embed", C.c_void_p), ("special_tokens", C.c_void_p)]
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [("verts", C.c_void_p), ("faces", C.c_void_p), ("colors", C.c_void_p), ("V", C.c_int),
+                ("F", C.c_int), ("poses", C.c_void_p), ("B", C.c_int), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("res", C.c_int), ("msaa", C.c_int),
+                ("cull_backfaces", C.c_int), ("gamma_lut", C.c_void_p), ("rgb", C.c_void_p),
+                ("depth", C.c_void_p)]
+
+
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "fp_abi_version": (_i, []),
+    "fp_last_error": (C.c_char_p, []),
+    "fp_device_sm_count": (_i, []),
+    "fp_vit_workspace_bytes": (_sz, [_i, _i]),
+    "fp_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "fp_gemm_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "fp_layernorm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
+    "fp_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    "fp_im2col_patches": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "fp_normalize_image": (_i, [_vp, _vp, _i, _i, _vp]),
+    "fp_score_workspace_bytes": (_sz, [_i, _i, _i]),
+    "fp_score_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "fp_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "fp_ffa_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "fp_raster_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "fp_rasterize": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp]),
+    "fp_mask_bbox": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fp_crop_resize_pad": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "fp_depth_extents": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library (building is an explicit step: ``python -m freepose_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("FREEPOSE_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m freepose_b200.build`.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fp_abi_version() != 1:
+        raise RuntimeError("libfreepose_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().fp_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("freepose_b200 kernels take CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("freepose_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,286 @@
+// Persistent, warp-specialised tcgen05 GEMM for the ViT linear layers:
+//
+//     C[M, N] = epilogue( A[M, K] (bf16, K contiguous)  x  W[N, K]^T (bf16, K contiguous) ),  fp32 accumulate
+//
+// One CTA per SM, 128 x 256 output tiles, K consumed in 64-element (128-byte, SWIZZLE_128B) slabs:
+//   warp 0        TMA producer      cp.async.bulk.tensor -> 4-stage smem ring (A 16 KB + W 32 KB per stage)
+//   warp 1        MMA issuer        one thread issues tcgen05.mma (M128 N256 K16) into TMEM
+//   warp 2        TMEM allocator    512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4..11   epilogue          tcgen05.ld -> registers -> fused epilogue -> bf16 global stores;
+//                                   overlaps the MMA of the next tile through the second accumulator
+//
+// Epilogues replicate the rounding points of PyTorch-eager bf16 (each ATen op rounds its output):
+//   BIAS          out = bf16(acc + b)                                            (attn.qkv)
+//   BIAS_GELU     out = bf16(gelu_erf(bf16(acc + b)))                            (mlp.fc1 + act)
+//   BIAS_LS_RES   out = bf16(res + bf16(bf16(acc + b) * gamma))                  (attn.proj / mlp.fc2 + LayerScale + residual)
+//   PATCH_EMBED   out[b*T + 1 + R + p] = bf16(bf16(acc + b) + pos[1 + p])        (patch-embed conv as GEMM + pos-embed)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Params {
+  int M, N, K;
+  bf16* out;
+  int ldo;  // output row stride (elements)
+  const bf16* bias;
+  const bf16* gamma;
+  const bf16* res;  // BIAS_LS_RES: residual [M, ldo] (may alias out); PATCH_EMBED: pos-embed [1 + P, N]
+  int patches_per_img;
+  int tokens_per_img;
+  int token_offset;
+};
+
+// erf with |abs err| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): far below half a bf16 ulp of the GELU output,
+// at ~12 issue slots instead of libdevice erff's ~25 (the fc1 epilogue must fit under the MMA time).
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
+
+__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erf_fast(u * 0.70710678118654752f)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m_tiles = (p.M + BM - 1) / BM;
+  const int num_n_tiles = p.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int kblocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * A_STAGE_BYTES), 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // +32 bytes per UMMA_K inside the 128-byte swizzle row -> +2 in the (addr >> 4) field
+            umma_bf16_ss(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // column half of the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      int out_row = row;
+      int pos_row = 0;
+      if (MODE == EPI_PATCH_EMBED) {
+        const int img = row / p.patches_per_img;
+        const int pidx = row - img * p.patches_per_img;
+        out_row = img * p.tokens_per_img + p.token_offset + pidx;
+        pos_row = 1 + pidx;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        const int col0 = half * 128 + chunk * 32;
+        const int gcol = n_blk * BN + col0;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
+        // operands that do not depend on the accumulator are fetched while the TMEM load is in flight
+        uint4 bv[4], gv[4], xv[4];
+        const uint4* bptr = reinterpret_cast<const uint4*>(p.bias + gcol);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bv[i] = __ldg(bptr + i);
+        if (MODE == EPI_BIAS_LS_RES) {
+          const uint4* gptr = reinterpret_cast<const uint4*>(p.gamma + gcol);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gv[i] = __ldg(gptr + i);
+          if (row_ok) {
+            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldo + gcol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xptr[i];
+          }
+        }
+        if (MODE == EPI_PATCH_EMBED) {
+          if (row_ok) {
+            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(pos_row) * p.N + gcol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = __ldg(xptr + i);
+          }
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+          uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
+            const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+            const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v0 = __uint_as_float(r[i * 8 + j * 2]) + bf16lo(bw[j]);
+              float v1 = __uint_as_float(r[i * 8 + j * 2 + 1]) + bf16hi(bw[j]);
+              if (MODE == EPI_BIAS_GELU) {
+                v0 = gelu_erf(bf16_round(v0));
+                v1 = gelu_erf(bf16_round(v1));
+              } else if (MODE == EPI_BIAS_LS_RES) {
+                v0 = bf16lo(xw[j]) + bf16_round(bf16_round(v0) * bf16lo(gw[j]));
+                v1 = bf16hi(xw[j]) + bf16_round(bf16_round(v1) * bf16hi(gw[j]));
+              } else if (MODE == EPI_PATCH_EMBED) {
+                v0 = bf16_round(v0) + bf16lo(xw[j]);
+                v1 = bf16_round(v1) + bf16hi(xw[j]);
+              }
+              ow[j] = pack_bf16x2(v0, v1);
+            }
+            optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int MODE>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    FP_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
+  FP_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  FP_REQUIRE(a.N % BN == 0, "gemm: N=%d must be a multiple of %d", a.N, BN);
+  FP_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d", a.K, BK);
+  FP_REQUIRE(a.A && a.W && a.out && a.bias, "gemm: null operand");
+  FP_REQUIRE(a.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_2d_bf16(&tmA, a.A, uint64_t(a.M), uint64_t(a.K), uint64_t(a.lda), BM, BK)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmB, a.W, uint64_t(a.N), uint64_t(a.K), uint64_t(a.K), BN, BK)) return rc;
+  Params p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.out = a.out; p.ldo = a.ldo;
+  p.bias = a.bias; p.gamma = a.gamma; p.res = a.res;
+  p.patches_per_img = a.patches_per_img > 0 ? a.patches_per_img : 1;
+  p.tokens_per_img = a.tokens_per_img;
+  p.token_offset = a.token_offset;
+  switch (a.mode) {
+    case EPI_BIAS: return launch<EPI_BIAS>(tmA, tmB, p, stream);
+    case EPI_BIAS_GELU: return launch<EPI_BIAS_GELU>(tmA, tmB, p, stream);
+    case EPI_BIAS_LS_RES:
+      FP_REQUIRE(a.gamma && a.res, "gemm: LayerScale/residual epilogue needs gamma and res");
+      return launch<EPI_BIAS_LS_RES>(tmA, tmB, p, stream);
+    case EPI_PATCH_EMBED:
+      FP_REQUIRE(a.res && a.tokens_per_img > 0, "gemm: patch-embed epilogue needs pos-embed and token layout");
+      return launch<EPI_PATCH_EMBED>(tmA, tmB, p, stream);
+  }
+  set_error("gemm: unknown epilogue mode %d", a.mode);
+  return -1;
+}
+
+}  // namespace fp

@@ -1,0 +1,105 @@
+// Internal C++ interface between the C ABI (capi.cu), the ViT engine (vit.cu) and the kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fp {
+
+typedef __nv_bfloat16 bf16;
+
+const char* last_error();
+
+// ---------------------------------------------------------------------------------------- GEMM
+enum EpilogueMode { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_LS_RES = 2, EPI_PATCH_EMBED = 3 };
+
+struct GemmArgs {
+  const bf16* A;   // [M, lda], K contiguous
+  int lda;
+  const bf16* W;   // [N, K], K contiguous (nn.Linear weight layout)
+  bf16* out;       // [*, ldo]
+  int ldo;
+  int M, N, K;
+  int mode;
+  const bf16* bias;   // [N]
+  const bf16* gamma;  // [N]             (EPI_BIAS_LS_RES)
+  const bf16* res;    // [M, ldo] residual (EPI_BIAS_LS_RES, may alias out) | pos-embed [1+P, N] (EPI_PATCH_EMBED)
+  int patches_per_img, tokens_per_img, token_offset;  // EPI_PATCH_EMBED row remap
+};
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- attention
+// qkv: [B*T, 3*H*64] bf16 (q | k | v, head-major inside each), out: [B*T, H*64] bf16.
+int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- elementwise
+// y = bf16(((x - mean) * rstd) * w + b), fp32 two-pass statistics, rows of D = 1024.
+// Row r of the output is written at out + (r / rows_per_group * out_group_stride + r % rows_per_group) * D
+// after skipping `in_skip` leading rows of every `in_group_stride`-row input group (used by the
+// final norm to drop cls + register tokens while normalising).
+int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int rows, int D, float eps,
+                   int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream);
+
+// Image (B, 3, res, res) -> patch matrix [B*g*g, Kpad] (col = c*196 + ky*14 + kx, zero padded).
+// src_is_f32 = 1: fp32 [0,1] image, the reference's bf16 Normalize is applied on the fly;
+// src_is_f32 = 0: already-normalised bf16 image.
+int im2col_patches(const void* img, int src_is_f32, bf16* out, int B, int res, int Kpad, cudaStream_t stream);
+
+// Float image in [0,1] (B,3,res,res) fp32 -> reference preprocessing in bf16:
+// x_bf16 = bf16(x); y = bf16(bf16(x_bf16 - bf16(mean_c)) / bf16(std_c))  (reference dino.py:12,16)
+int normalize_image(const float* img, bf16* out, int B, int res, cudaStream_t stream);
+
+// Rows 0..R of every image's token block: special[(1+R), D] (cls+pos[0], registers) broadcast.
+int write_special_tokens(const bf16* special, bf16* tokens, int B, int T, int n_special, int D, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- score
+// Position-aligned per-patch cosine (reference pose_estimator.py:85-90).  See score.cu.
+int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D,
+               int normalise_query, float* scores_out, float* patch_scores_out, int k, int* topk_idx,
+               float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t score_workspace_bytes(int B, int P, int D);
+int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val, void* workspace,
+              size_t workspace_bytes, cudaStream_t stream);
+
+// FFA pooling (reference extract_retrieval_features.py:49-57)
+int ffa_pool(const bf16* feats, const uint8_t* masks, int V, int res, int g, int D, float* out,
+             int* valid, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- raster
+struct RasterArgs {
+  const float* verts;     // [V, 3] fp32 object-space
+  const int32_t* faces;   // [F, 3]
+  const uint8_t* colors;  // [V, 3] u8 vertex colours
+  int V, F;
+  const float* poses;     // [B, 12] row-major 3x4 (R | t), object -> OpenCV camera
+  int B;
+  float fx, fy, cx, cy;
+  int res;
+  int msaa;               // 1 or 4
+  int cull_backfaces;
+  const uint8_t* gamma_lut;  // [65536] u8
+  uint8_t* rgb;           // [B, res, res, 3] u8
+  float* depth;           // [B, res, res] fp32 metres, 0 = background
+};
+int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes);
+int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- geometry
+int mask_bbox(const float* depth, int B, int res, int fallback_lo, int fallback_hi, int min_count,
+              int32_t* bbox_out, int32_t* count_out, uint8_t* mask_out, cudaStream_t stream);
+int crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, const bf16* norm_lut, void* dst,
+                    int dst_is_patches, int B, int src_h, int src_w, int T, int Kpad, int32_t* status,
+                    cudaStream_t stream);
+int depth_extents(const float* depth, const int32_t* view_idx, int n_out, int res, const double* kinv_dev,
+                  double* out, cudaStream_t stream);
+
+}  // namespace fp
+
+// ---------------------------------------------------------------------------------------- ViT
+struct fp_vit_weights;
+namespace fp {
+size_t vit_workspace_bytes(int B, int res);
+int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int B, int res, int layer,
+                int feature_type, void* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+}  // namespace fp

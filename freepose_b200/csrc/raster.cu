@@ -1,0 +1,340 @@
+// Batched triangle rasteriser for pose-hypothesis views (replaces the per-pose
+// pyrender/OpenGL draw + glReadPixels loop of reference src/pipeline/retrieval/renderer.py:43-95).
+//
+// Semantics restated from the reference's pyrender set-up (renderer.py:37-66):
+//   * pinhole camera (fx, fy, cx, cy), OpenCV camera frame (the reference's camera node pose diag(1,-1,-1,1)
+//     makes world == OpenCV camera); window coordinate u = fx*X/Z + cx, pixel i covers [i, i+1);
+//   * ambient-only lighting (2,2,2): colour = clamp(pow(2 * base_colour, 1/2.2), 0, 1) -> unorm8; transparent
+//     black background; SKIP_CULL_FACES (two-sided) unless cull_backfaces;
+//   * 4x multisampling (pyrender's offscreen framebuffer): coverage and depth per sample, one shading
+//     evaluation per (triangle, pixel) at the pixel centre, box-filter resolve in unorm8; the depth image is
+//     sample 0's linear depth (0 = background).  msaa = 1 evaluates everything at the pixel centre.
+//
+// Everything that decides *which* triangle a sample sees is integer arithmetic (24.8 fixed-point vertices,
+// 64-bit edge functions, top-left rule) and the depth test is an order-independent 64-bit atomicMin on
+// (depth bits, face id), so results are deterministic and the CPU oracle (oracle/raster_ref.c) restates them
+// bit for bit.  All fp32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction).
+//
+// Kernels: clear keys -> vertex transform -> triangle scatter (warp-cooperative for large triangles) ->
+// resolve (4 pixels per thread, 12-byte RGB + 16-byte depth vector stores).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fp {
+
+namespace {
+
+constexpr int SUB = 8;                 // sub-pixel bits
+constexpr int ONE = 1 << SUB;          // 256
+constexpr float ZNEAR = 0.05f;         // pyrender IntrinsicsCamera default
+constexpr float ZFAR = 100.0f;
+constexpr int COORD_LIMIT = 1 << 22;   // |fixed-point coordinate| guard (16384 px)
+
+struct __align__(16) ScreenVertex {
+  int x, y;      // 24.8 fixed point, image coordinates (y down)
+  float z;       // camera-space depth
+  float iz;      // 1 / z
+};
+
+__constant__ int c_sample_off[2][4][2] = {
+    {{128, 128}, {128, 128}, {128, 128}, {128, 128}},   // msaa 1: pixel centre
+    {{96, 32}, {224, 96}, {32, 160}, {160, 224}},       // msaa 4: (0.375,0.125) (0.875,0.375) (0.125,0.625) (0.625,0.875)
+};
+
+__global__ void __launch_bounds__(256)
+clear_keys_kernel(unsigned long long* __restrict__ keys, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = ~0ull;
+}
+
+__global__ void __launch_bounds__(256)
+vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, ScreenVertex* __restrict__ sv,
+              int V, int B, float fx, float fy, float cx, float cy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= V) return;
+  const float* P = poses + size_t(b) * 12;
+  const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+  // cam = R * v + t, evaluated as ((r0*x + r1*y) + r2*z) + t
+  const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], x), __fmul_rn(P[1], y)), __fmul_rn(P[2], z)), P[3]);
+  const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4], x), __fmul_rn(P[5], y)), __fmul_rn(P[6], z)), P[7]);
+  const float Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[8], x), __fmul_rn(P[9], y)), __fmul_rn(P[10], z)), P[11]);
+  ScreenVertex o;
+  if (!(Z > ZNEAR) || !(Z < ZFAR)) {
+    o.x = INT_MIN; o.y = INT_MIN; o.z = 0.f; o.iz = 0.f;
+  } else {
+    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(fx, X), Z), cx);
+    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(fy, Y), Z), cy);
+    const float uf = floorf(__fadd_rn(__fmul_rn(u, float(ONE)), 0.5f));
+    const float vf = floorf(__fadd_rn(__fmul_rn(v, float(ONE)), 0.5f));
+    if (!(fabsf(uf) < float(COORD_LIMIT)) || !(fabsf(vf) < float(COORD_LIMIT))) {
+      o.x = INT_MIN; o.y = INT_MIN; o.z = 0.f; o.iz = 0.f;
+    } else {
+      o.x = int(uf); o.y = int(vf); o.z = Z; o.iz = __fdiv_rn(1.0f, Z);
+    }
+  }
+  sv[size_t(b) * V + i] = o;
+}
+
+struct TriSetup {
+  // edge functions E_i(p) = A_i * px + B_i * py + C_i (64-bit), fill-rule bias folded into C
+  long long A[3], Bc[3], C[3];
+  float z[3], iz[3];
+  float area;
+  int xmin, xmax, ymin, ymax;  // inclusive pixel bbox, already clipped
+  int valid;
+};
+
+__device__ __forceinline__ bool setup_triangle(const ScreenVertex& a0, const ScreenVertex& a1, const ScreenVertex& a2,
+                                               int res, int cull, TriSetup& t) {
+  if (a0.x == INT_MIN || a1.x == INT_MIN || a2.x == INT_MIN) return false;
+  ScreenVertex v0 = a0, v1 = a1, v2 = a2;
+  long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
+  if (area == 0) return false;
+  // image coordinates have y down: GL-front-facing (CCW in the y-up window) <=> area < 0 here
+  if (cull && area > 0) return false;
+  if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; area = -area; }
+  const int minx = min(v0.x, min(v1.x, v2.x)), maxx = max(v0.x, max(v1.x, v2.x));
+  const int miny = min(v0.y, min(v1.y, v2.y)), maxy = max(v0.y, max(v1.y, v2.y));
+  // pixels whose [px, px+1) square can contain a sample inside [min, max]
+  t.xmin = max(0, minx >> SUB); t.xmax = min(res - 1, maxx >> SUB);
+  t.ymin = max(0, miny >> SUB); t.ymax = min(res - 1, maxy >> SUB);
+  if (t.xmin > t.xmax || t.ymin > t.ymax) return false;
+  const ScreenVertex* e0[3] = {&v1, &v2, &v0};  // edge i runs e0[i] -> e1[i]; weight i belongs to vertex i
+  const ScreenVertex* e1[3] = {&v2, &v0, &v1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const long long dx = e1[i]->x - e0[i]->x, dy = e1[i]->y - e0[i]->y;
+    // E(p) = dx * (py - ay) - dy * (px - ax)  > 0 inside (orientation normalised above)
+    t.A[i] = -dy;
+    t.Bc[i] = dx;
+    t.C[i] = dy * e0[i]->x - dx * e0[i]->y;
+    const bool topleft = (dy < 0) || (dy == 0 && dx > 0);
+    if (!topleft) t.C[i] -= 1;  // then "E >= 0" implements the top-left rule
+  }
+  t.z[0] = v0.z; t.z[1] = v1.z; t.z[2] = v2.z;
+  t.iz[0] = v0.iz; t.iz[1] = v1.iz; t.iz[2] = v2.iz;
+  t.area = __ll2float_rn(area);
+  t.valid = 1;
+  return true;
+}
+
+// Depth of the triangle at a sample from its three (biased) edge values -- perspective correct:
+// 1/z is affine in screen space.
+__device__ __forceinline__ float sample_depth(const TriSetup& t, long long e0, long long e1, long long e2,
+                                              const long long* bias) {
+  const float w0 = __fdiv_rn(__ll2float_rn(e0 + bias[0]), t.area);
+  const float w1 = __fdiv_rn(__ll2float_rn(e1 + bias[1]), t.area);
+  const float w2 = __fdiv_rn(__ll2float_rn(e2 + bias[2]), t.area);
+  const float iz = __fadd_rn(__fadd_rn(__fmul_rn(w0, t.iz[0]), __fmul_rn(w1, t.iz[1])), __fmul_rn(w2, t.iz[2]));
+  return __fdiv_rn(1.0f, iz);
+}
+
+template <int S>
+__device__ __forceinline__ void raster_pixel(const TriSetup& t, const long long* bias, int px, int py,
+                                             unsigned long long* __restrict__ keys_view, int res, unsigned face) {
+  const long long bx = (long long)px << SUB, by = (long long)py << SUB;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const long long sx = bx + c_sample_off[S == 4][s][0], sy = by + c_sample_off[S == 4][s][1];
+    const long long e0 = t.A[0] * sx + t.Bc[0] * sy + t.C[0];
+    const long long e1 = t.A[1] * sx + t.Bc[1] * sy + t.C[1];
+    const long long e2 = t.A[2] * sx + t.Bc[2] * sy + t.C[2];
+    if ((e0 | e1 | e2) >= 0) {
+      const float z = sample_depth(t, e0, e1, e2, bias);
+      if (z > ZNEAR && z < ZFAR) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | face;
+        atomicMin(&keys_view[(size_t(py) * res + px) * S + s], key);
+      }
+    }
+  }
+}
+
+constexpr int BIG_TRI_PIXELS = 64;
+
+template <int S>
+__global__ void __launch_bounds__(256)
+triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ faces,
+                unsigned long long* __restrict__ keys, int V, int F, int res, int cull) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const ScreenVertex* svb = sv + size_t(b) * V;
+  unsigned long long* keys_view = keys + size_t(b) * res * res * S;
+  TriSetup t;
+  t.valid = 0;
+  long long bias[3] = {0, 0, 0};
+  if (f < F) {
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    if (setup_triangle(svb[i0], svb[i1], svb[i2], res, cull, t)) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const long long dx = t.Bc[i], dy = -t.A[i];
+        bias[i] = ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;  // undo the fill-rule bias for interpolation
+      }
+    }
+  }
+  const int w = t.valid ? (t.xmax - t.xmin + 1) : 0;
+  const int h = t.valid ? (t.ymax - t.ymin + 1) : 0;
+  const bool big = w * h > BIG_TRI_PIXELS;
+  if (t.valid && !big) {
+    for (int py = t.ymin; py <= t.ymax; ++py)
+      for (int px = t.xmin; px <= t.xmax; ++px) raster_pixel<S>(t, bias, px, py, keys_view, res, unsigned(f));
+  }
+  // large triangles: the whole warp walks the bounding box of one triangle at a time
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    TriSetup u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      u.A[i] = __shfl_sync(0xffffffffu, t.A[i], src);
+      u.Bc[i] = __shfl_sync(0xffffffffu, t.Bc[i], src);
+      u.C[i] = __shfl_sync(0xffffffffu, t.C[i], src);
+      u.z[i] = __shfl_sync(0xffffffffu, t.z[i], src);
+      u.iz[i] = __shfl_sync(0xffffffffu, t.iz[i], src);
+    }
+    long long ub[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ub[i] = __shfl_sync(0xffffffffu, bias[i], src);
+    u.area = __shfl_sync(0xffffffffu, t.area, src);
+    u.xmin = __shfl_sync(0xffffffffu, t.xmin, src);
+    u.ymin = __shfl_sync(0xffffffffu, t.ymin, src);
+    const int uw = __shfl_sync(0xffffffffu, w, src), uh = __shfl_sync(0xffffffffu, h, src);
+    const unsigned uf = unsigned(__shfl_sync(0xffffffffu, f, src));
+    for (int i = lane; i < uw * uh; i += 32) {
+      const int py = u.ymin + i / uw, px = u.xmin + i % uw;
+      raster_pixel<S>(u, ub, px, py, keys_view, res, uf);
+    }
+  }
+}
+
+// Shade triangle `face` at the centre of pixel (px, py): perspective-correct vertex-colour interpolation,
+// x2 ambient, gamma LUT -> unorm8.
+__device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, const int* __restrict__ faces,
+                                      const uint8_t* __restrict__ colors, const uint8_t* __restrict__ lut,
+                                      unsigned face, int px, int py, int out[3]) {
+  const int i0 = faces[3 * face], i1 = faces[3 * face + 1], i2 = faces[3 * face + 2];
+  ScreenVertex v0 = svb[i0], v1 = svb[i1], v2 = svb[i2];
+  int c0 = i0, c1 = i1, c2 = i2;
+  long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
+  if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
+  const long long sx = ((long long)px << SUB) + 128, sy = ((long long)py << SUB) + 128;
+  // unbiased edge values (may be negative: the centre can lie outside a partially covered pixel's triangle)
+  const long long e0 = (long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x);
+  const long long e1 = (long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x);
+  const long long e2 = (long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x);
+  const float fa = __ll2float_rn(area);
+  const float w0 = __fmul_rn(__fdiv_rn(__ll2float_rn(e0), fa), v0.iz);
+  const float w1 = __fmul_rn(__fdiv_rn(__ll2float_rn(e1), fa), v1.iz);
+  const float w2 = __fmul_rn(__fdiv_rn(__ll2float_rn(e2), fa), v2.iz);
+  const float wsum = __fadd_rn(__fadd_rn(w0, w1), w2);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float a0 = float(colors[3 * c0 + ch]), a1 = float(colors[3 * c1 + ch]), a2 = float(colors[3 * c2 + ch]);
+    float c = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, a0), __fmul_rn(w1, a1)), __fmul_rn(w2, a2)), wsum);
+    // base colour in [0,1] is c/255; ambient (2,2,2): linear = 2c/255, clamped; LUT index = round(linear*65535)
+    float lin = __fmul_rn(c, 2.0f / 255.0f);
+    lin = fminf(fmaxf(lin, 0.f), 1.f);
+    if (!(lin == lin)) lin = 0.f;
+    const int idx = int(__fadd_rn(__fmul_rn(lin, 65535.0f), 0.5f));
+    out[ch] = lut[idx];
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256)
+resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
+               const int* __restrict__ faces, const uint8_t* __restrict__ colors, const uint8_t* __restrict__ lut,
+               uint8_t* __restrict__ rgb, float* __restrict__ depth, int V, int res) {
+  const int b = blockIdx.y;
+  const int quads_per_row = res >> 2;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= quads_per_row * res) return;
+  const int py = qi / quads_per_row, px0 = (qi - py * quads_per_row) << 2;
+  const ScreenVertex* svb = sv + size_t(b) * V;
+  const unsigned long long* kv = keys + (size_t(b) * res * res + size_t(py) * res + px0) * S;
+  uint8_t pix[12];
+  float dep[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unsigned long long k[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) k[s] = kv[i * S + s];
+    int acc[3] = {0, 0, 0};
+    unsigned last_face = 0xffffffffu;
+    int col[3] = {0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (k[s] != ~0ull) {
+        const unsigned face = unsigned(k[s] & 0xffffffffu);
+        if (face != last_face) {
+          shade(svb, faces, colors, lut, face, px0 + i, py, col);
+          last_face = face;
+        }
+        acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2];
+      }
+    }
+    if (S == 4) {
+      pix[3 * i] = uint8_t((acc[0] + 2) >> 2);
+      pix[3 * i + 1] = uint8_t((acc[1] + 2) >> 2);
+      pix[3 * i + 2] = uint8_t((acc[2] + 2) >> 2);
+    } else {
+      pix[3 * i] = uint8_t(acc[0]); pix[3 * i + 1] = uint8_t(acc[1]); pix[3 * i + 2] = uint8_t(acc[2]);
+    }
+    dep[i] = (k[0] != ~0ull) ? __uint_as_float(unsigned(k[0] >> 32)) : 0.f;
+  }
+  uint32_t* o = reinterpret_cast<uint32_t*>(rgb + (size_t(b) * res * res + size_t(py) * res + px0) * 3);
+  o[0] = pix[0] | (pix[1] << 8) | (pix[2] << 16) | (uint32_t(pix[3]) << 24);
+  o[1] = pix[4] | (pix[5] << 8) | (pix[6] << 16) | (uint32_t(pix[7]) << 24);
+  o[2] = pix[8] | (pix[9] << 8) | (pix[10] << 16) | (uint32_t(pix[11]) << 24);
+  *reinterpret_cast<float4*>(depth + size_t(b) * res * res + size_t(py) * res + px0) =
+      make_float4(dep[0], dep[1], dep[2], dep[3]);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
+  FP_REQUIRE(msaa == 1 || msaa == 4, "raster: msaa must be 1 or 4");
+  FP_REQUIRE(B >= 0 && V >= 0 && res > 0, "raster: bad sizes");
+  *bytes = align_up(size_t(B) * V * sizeof(ScreenVertex), 256) + size_t(B) * res * res * msaa * 8 + 256;
+  return 0;
+}
+
+int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(a.res > 0 && a.res % 4 == 0, "raster: resolution %d must be a positive multiple of 4", a.res);
+  FP_REQUIRE(a.msaa == 1 || a.msaa == 4, "raster: msaa must be 1 or 4");
+  FP_REQUIRE(a.V > 0 && a.F > 0, "raster: empty mesh (V=%d, F=%d)", a.V, a.F);
+  FP_REQUIRE(a.B <= 65535, "raster: at most 65535 views per call");
+  if (a.B <= 0) return 0;
+  size_t need = 0;
+  if (int rc = raster_workspace_bytes(a.B, a.V, a.res, a.msaa, &need)) return rc;
+  FP_REQUIRE(workspace_bytes >= need, "raster: workspace too small (%zu < %zu)", workspace_bytes, need);
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "raster: workspace must be 256-byte aligned");
+  ScreenVertex* sv = reinterpret_cast<ScreenVertex*>(workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(
+      reinterpret_cast<uint8_t*>(workspace) + align_up(size_t(a.B) * a.V * sizeof(ScreenVertex), 256));
+  const size_t nkeys = size_t(a.B) * a.res * a.res * a.msaa;
+  clear_keys_kernel<<<sm_count() * 8, 256, 0, stream>>>(keys, nkeys);
+  FP_CUDA(cudaGetLastError());
+  vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy);
+  FP_CUDA(cudaGetLastError());
+  const dim3 tgrid((a.F + 255) / 256, a.B);
+  const dim3 rgrid((a.res * a.res / 4 + 255) / 256, a.B);
+  if (a.msaa == 4) {
+    triangle_kernel<4><<<tgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces);
+    FP_CUDA(cudaGetLastError());
+    resolve_kernel<4><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, a.colors, a.gamma_lut, a.rgb, a.depth, a.V, a.res);
+  } else {
+    triangle_kernel<1><<<tgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces);
+    FP_CUDA(cudaGetLastError());
+    resolve_kernel<1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, a.colors, a.gamma_lut, a.rgb, a.depth, a.V, a.res);
+  }
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp

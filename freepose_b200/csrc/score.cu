@@ -1,0 +1,284 @@
+// Per-hypothesis score + top-k.
+//
+// Reference arithmetic (pose_estimator.py:85-90, online_pose_estimator.py:68-79), model dtype bf16:
+//     tn = F.normalize(feats_t, dim=-1)   -> norm = bf16(sqrt(sum t^2)); tn = bf16(t / max(norm, eps))
+//     qn = F.normalize(query,  dim=-1)
+//     s  = einsum('b n d, b n d -> b n')  -> bf16(sum_d tn*qn)        (fp32 accumulate)
+//     score = s.mean(-1)                  -> bf16(sum_n s / P)        (fp32 accumulate)
+//     fine / mask_scores:  score = sum_n(s*w) / sum_n(w) in fp32
+// The kernel reproduces those rounding points and FIXES the fp32 summation order so that the CPU
+// oracle (oracle/score.py, "engine order") can restate it bit-exactly:
+//   * a D-long reduction: lane l accumulates elements c*256 + l*8 + j (c outer, j = 0..7 inner) with
+//     acc = acc + a*b (a*b is exact in fp32 for bf16 inputs), then the xor-butterfly 16,8,4,2,1;
+//   * a P-long reduction: lane l accumulates n = l, l+32, ... ascending, then the same butterfly.
+// HBM-bound: every template token row (2 KB) is read exactly once; one CTA per hypothesis.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fp {
+
+namespace {
+
+constexpr int SC_WARPS = 8;
+constexpr int MAX_CHUNKS = 4;  // D <= 1024
+
+__device__ __forceinline__ void load_row(const bf16* row, int lane, int chunks, uint4 (&u)[MAX_CHUNKS]) {
+  const uint4* p = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int c = 0; c < MAX_CHUNKS; ++c)
+    if (c < chunks) u[c] = p[c * 32 + lane];
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+
+// bf16(sqrt(sum x^2)) clamped below by bf16(eps), as float
+__device__ __forceinline__ float row_norm(const uint4 (&u)[MAX_CHUNKS], int chunks) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAX_CHUNKS; ++c)
+    if (c < chunks) {
+      float f[8];
+      unpack8(u[c], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, __fmul_rn(f[j], f[j]));
+    }
+  acc = warp_sum(acc);
+  const float nrm = bf16_round(__fsqrt_rn(acc));
+  const float eps = bf16_round(1e-12f);
+  return fmaxf(nrm, eps);
+}
+
+// qn = normalised (or verbatim) query tokens, one warp per row
+__global__ void __launch_bounds__(SC_WARPS * 32)
+prep_query_kernel(const bf16* __restrict__ q, bf16* __restrict__ qn, int P, int D, int normalise) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * SC_WARPS + warp;
+  if (n >= P) return;
+  const int chunks = D / 256;
+  uint4 u[MAX_CHUNKS];
+  load_row(q + size_t(n) * D, lane, chunks, u);
+  uint4* op = reinterpret_cast<uint4*>(qn + size_t(n) * D);
+  if (!normalise) {
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c)
+      if (c < chunks) op[c * 32 + lane] = u[c];
+    return;
+  }
+  const float nrm = row_norm(u, chunks);
+#pragma unroll
+  for (int c = 0; c < MAX_CHUNKS; ++c)
+    if (c < chunks) {
+      float f[8];
+      unpack8(u[c], f);
+      uint4 o;
+      o.x = pack_bf16x2(__fdiv_rn(f[0], nrm), __fdiv_rn(f[1], nrm));
+      o.y = pack_bf16x2(__fdiv_rn(f[2], nrm), __fdiv_rn(f[3], nrm));
+      o.z = pack_bf16x2(__fdiv_rn(f[4], nrm), __fdiv_rn(f[5], nrm));
+      o.w = pack_bf16x2(__fdiv_rn(f[6], nrm), __fdiv_rn(f[7], nrm));
+      op[c * 32 + lane] = o;
+    }
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
+score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, const float* __restrict__ weights,
+             int P, int D, float* __restrict__ scores, float* __restrict__ patch_scores) {
+  extern __shared__ float s_patch[];  // [P] bf16-valued per-patch cosines
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int chunks = D / 256;
+  const bf16* base = feats_t + size_t(b) * P * D;
+  for (int n = warp; n < P; n += SC_WARPS) {
+    uint4 t[MAX_CHUNKS], q[MAX_CHUNKS];
+    load_row(base + size_t(n) * D, lane, chunks, t);
+    load_row(qn + size_t(n) * D, lane, chunks, q);
+    const float nrm = row_norm(t, chunks);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c)
+      if (c < chunks) {
+        float tf[8], qf[8];
+        unpack8(t[c], tf);
+        unpack8(q[c], qf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float tn = bf16_round(__fdiv_rn(tf[j], nrm));
+          acc = __fadd_rn(acc, __fmul_rn(tn, qf[j]));
+        }
+      }
+    acc = warp_sum(acc);
+    if (lane == 0) s_patch[n] = bf16_round(acc);
+  }
+  __syncthreads();
+  if (patch_scores != nullptr)
+    for (int n = threadIdx.x; n < P; n += blockDim.x) patch_scores[size_t(b) * P + n] = s_patch[n];
+  if (warp == 0) {
+    if (weights == nullptr) {
+      float acc = 0.f;
+      for (int n = lane; n < P; n += 32) acc = __fadd_rn(acc, s_patch[n]);
+      acc = warp_sum(acc);
+      if (lane == 0) scores[b] = bf16_round(__fdiv_rn(acc, float(P)));
+    } else {
+      const float* w = weights + size_t(b) * P;
+      float num = 0.f, den = 0.f;
+      for (int n = lane; n < P; n += 32) {
+        const float wn = w[n];
+        num = __fadd_rn(num, __fmul_rn(s_patch[n], wn));
+        den = __fadd_rn(den, wn);
+      }
+      num = warp_sum(num);
+      den = warp_sum(den);
+      if (lane == 0) scores[b] = __fdiv_rn(num, den);
+    }
+  }
+}
+
+// Deterministic top-k: descending value, ties -> lowest index (NaN sorts first, like torch.topk).
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn != bn) return vn;
+  if (!vn && v != bv) return v > bv;
+  return i < bi;
+}
+
+__global__ void __launch_bounds__(1024)
+topk_kernel(const float* __restrict__ scores, int B, int k, int* __restrict__ idx_out, float* __restrict__ val_out,
+            uint8_t* __restrict__ taken) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) taken[i] = 0;
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    float bv = 0.f;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < B; i += blockDim.x)
+      if (!taken[i]) {
+        const float v = scores[i];
+        if (bi == 0x7fffffff || better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = sv[lane];
+      bi = si[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi != 0x7fffffff) {
+          idx_out[r] = bi;
+          val_out[r] = bv;
+          taken[bi] = 1;
+        } else {
+          idx_out[r] = -1;
+          val_out[r] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// FFA pooling: mask (res x res, u8) -> 14x14 max-pool -> mean of the selected patch tokens.
+// Reference (extract_retrieval_features.py:51-57): cv2.resize(mask, (g, g), INTER_AREA) > 0 is true
+// exactly when any pixel of the 14x14 cell is set; feat[mask].mean(0) on bf16 rounds the fp32-accumulated
+// mean to bf16, then .float().  Order: patches ascending, acc = acc + x.
+__global__ void __launch_bounds__(256)
+ffa_kernel(const bf16* __restrict__ feats, const uint8_t* __restrict__ masks, int res, int g, int D,
+           float* __restrict__ out, int* __restrict__ valid) {
+  extern __shared__ uint8_t cell[];  // [g*g]
+  const int v = blockIdx.x;
+  const uint8_t* m = masks + size_t(v) * res * res;
+  const int P = g * g;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) {
+    const int cy = c / g, cx = c - cy * g;
+    int any = 0;
+    for (int y = 0; y < 14; ++y) {
+      const uint8_t* rowp = m + size_t(cy * 14 + y) * res + cx * 14;
+#pragma unroll
+      for (int x = 0; x < 14; ++x) any |= rowp[x];
+    }
+    cell[c] = any ? 1 : 0;
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int c = 0; c < P; ++c) cnt += cell[c];
+  const bf16* f = feats + size_t(v) * P * D;
+  for (int d = threadIdx.x * 2; d < D; d += blockDim.x * 2) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = 0; c < P; ++c)
+      if (cell[c]) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(f + size_t(c) * D + d);
+        a0 = __fadd_rn(a0, bf16lo(u));
+        a1 = __fadd_rn(a1, bf16hi(u));
+      }
+    // empty mask -> 0/0 = NaN, which the reference detects and skips (extract_retrieval_features.py:59-65)
+    out[size_t(v) * D + d] = bf16_round(__fdiv_rn(a0, float(cnt)));
+    out[size_t(v) * D + d + 1] = bf16_round(__fdiv_rn(a1, float(cnt)));
+  }
+  if (threadIdx.x == 0 && valid != nullptr) valid[v] = cnt;
+}
+
+}  // namespace
+
+size_t score_workspace_bytes(int B, int P, int D) {
+  return size_t(P) * D * sizeof(bf16) + size_t(B) + 256;
+}
+
+int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D,
+               int normalise_query, float* scores_out, float* patch_scores_out, int k, int* topk_idx,
+               float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(D % 256 == 0 && D <= 256 * MAX_CHUNKS, "score: D=%d must be a multiple of 256 and <= 1024", D);
+  FP_REQUIRE(B >= 0 && P > 0, "score: bad shape B=%d P=%d", B, P);
+  FP_REQUIRE(k >= 0 && k <= B, "score: k=%d out of range for B=%d hypotheses", k, B);
+  FP_REQUIRE(workspace_bytes >= score_workspace_bytes(B, P, D), "score: workspace too small");
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "score: workspace must be 16-byte aligned");
+  if (B == 0) return 0;
+  bf16* qn = reinterpret_cast<bf16*>(workspace);
+  uint8_t* taken = reinterpret_cast<uint8_t*>(workspace) + size_t(P) * D * sizeof(bf16);
+  prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query);
+  FP_CUDA(cudaGetLastError());
+  const size_t smem = size_t(P) * sizeof(float);
+  FP_REQUIRE(smem <= 48 * 1024, "score: P=%d too large", P);
+  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, scores_out, patch_scores_out);
+  FP_CUDA(cudaGetLastError());
+  if (k > 0) {
+    topk_kernel<<<1, 1024, 0, stream>>>(scores_out, B, k, topk_idx, topk_val, taken);
+    FP_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val, void* workspace,
+              size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(k >= 0 && k <= B, "topk: k=%d out of range for B=%d", k, B);
+  FP_REQUIRE(workspace_bytes >= size_t(B), "topk: workspace too small");
+  if (k == 0) return 0;
+  topk_kernel<<<1, 1024, 0, stream>>>(scores, B, k, topk_idx, topk_val, reinterpret_cast<uint8_t*>(workspace));
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ffa_pool(const bf16* feats, const uint8_t* masks, int V, int res, int g, int D, float* out, int* valid,
+             cudaStream_t stream) {
+  FP_REQUIRE(res == g * 14, "ffa: mask resolution %d != 14 * grid %d", res, g);
+  FP_REQUIRE(D % 2 == 0, "ffa: D must be even");
+  if (V <= 0) return 0;
+  ffa_kernel<<<V, 256, size_t(g) * g, stream>>>(feats, masks, res, g, D, out, valid);
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fp

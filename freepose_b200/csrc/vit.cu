@@ -1,0 +1,105 @@
+// DINOv2 ViT-L/14-reg forward to layer L + final norm (reference src/pipeline/retrieval/dino.py:14-32):
+// sequencing of the kernels over caller-provided workspace.  Stateless: weights and buffers are borrowed
+// device pointers (include/freepose_b200.h: fp_vit_weights / fp_vit_forward).
+#include "common.cuh"
+#include "kernels.h"
+#include "freepose_b200.h"
+
+namespace fp {
+
+namespace {
+constexpr int D = 1024, HEADS = 16, MLP = 4096, KPAD = 640, NREG = 4;
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+size_t vit_workspace_bytes(int B, int res) {
+  const int g = res / 14, P = g * g, T = P + 1 + NREG;
+  const size_t M = size_t(B) * T;
+  return align256(M * D * 2) * 2        // residual stream x, scratch h
+         + align256(M * 3 * D * 2)      // qkv
+         + align256(M * MLP * 2)        // mlp hidden
+         + align256(size_t(B) * P * KPAD * 2)  // patch matrix
+         + 256;
+}
+
+int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int B, int res, int layer,
+                int feature_type, void* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(w != nullptr && w->layers != nullptr, "vit: null weights");
+  FP_REQUIRE(res > 0 && res % 14 == 0, "vit: crop resolution %d is not a multiple of the 14-pixel patch", res);
+  FP_REQUIRE(layer >= 0 && layer <= w->depth, "vit: layer %d outside [0, %d]", layer, w->depth);
+  FP_REQUIRE(w->pos_res == res, "vit: position embedding was prepared for %d px crops, got %d", w->pos_res, res);
+  FP_REQUIRE(input_kind >= 0 && input_kind <= 2, "vit: unknown input kind %d", input_kind);
+  FP_REQUIRE(feature_type >= 0 && feature_type <= 3, "vit: unknown feature type %d", feature_type);
+  if (B <= 0) return 0;
+  const int g = res / 14, P = g * g, T = P + 1 + NREG;
+  const size_t M = size_t(B) * T;
+  FP_REQUIRE(M < (size_t(1) << 31) / 4, "vit: batch too large for one call");
+  FP_REQUIRE(workspace_bytes >= vit_workspace_bytes(B, res), "vit: workspace too small (%zu < %zu)", workspace_bytes,
+             vit_workspace_bytes(B, res));
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vit: workspace must be 256-byte aligned");
+
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  bf16* x = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
+  bf16* h = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
+  bf16* qkv = reinterpret_cast<bf16*>(ws); ws += align256(M * 3 * D * 2);
+  bf16* mlp = reinterpret_cast<bf16*>(ws); ws += align256(M * MLP * 2);
+  bf16* patches = reinterpret_cast<bf16*>(ws);
+
+  // ---- tokens: patch-embed GEMM (+bias, +pos-embed, scattered behind the cls/register rows)
+  const bf16* pm = patches;
+  if (input_kind == FP_INPUT_PATCHES) {
+    pm = reinterpret_cast<const bf16*>(input);
+  } else {
+    if (int rc = im2col_patches(input, input_kind == FP_INPUT_IMAGE_F32, patches, B, res, KPAD, stream)) return rc;
+  }
+  if (int rc = write_special_tokens(reinterpret_cast<const bf16*>(w->special_tokens), x, B, T, 1 + NREG, D, stream))
+    return rc;
+  {
+    GemmArgs a{};
+    a.A = pm; a.lda = KPAD; a.W = reinterpret_cast<const bf16*>(w->patch_w);
+    a.out = x; a.ldo = D; a.M = B * P; a.N = D; a.K = KPAD; a.mode = EPI_PATCH_EMBED;
+    a.bias = reinterpret_cast<const bf16*>(w->patch_b);
+    a.res = reinterpret_cast<const bf16*>(w->pos_embed);
+    a.patches_per_img = P; a.tokens_per_img = T; a.token_offset = 1 + NREG;
+    if (int rc = gemm_bf16(a, stream)) return rc;
+  }
+
+  // ---- transformer blocks
+  const float scale = 0.125f;  // head_dim^-0.5
+  for (int l = 0; l < layer; ++l) {
+    const fp_vit_layer& L = w->layers[l];
+    auto P16 = [](const void* p) { return reinterpret_cast<const bf16*>(p); };
+    if (int rc = layernorm_bf16(x, P16(L.ln1_w), P16(L.ln1_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
+    GemmArgs a{};
+    a.A = h; a.lda = D; a.W = P16(L.qkv_w); a.out = qkv; a.ldo = 3 * D; a.M = int(M); a.N = 3 * D; a.K = D;
+    a.mode = EPI_BIAS; a.bias = P16(L.qkv_b);
+    if (int rc = gemm_bf16(a, stream)) return rc;
+    if (int rc = attention_bf16(qkv, h, B, T, HEADS, scale, stream)) return rc;
+    a = GemmArgs{};
+    a.A = h; a.lda = D; a.W = P16(L.proj_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = D;
+    a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.proj_b); a.gamma = P16(L.ls1); a.res = x;
+    if (int rc = gemm_bf16(a, stream)) return rc;
+    if (int rc = layernorm_bf16(x, P16(L.ln2_w), P16(L.ln2_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
+    a = GemmArgs{};
+    a.A = h; a.lda = D; a.W = P16(L.fc1_w); a.out = mlp; a.ldo = MLP; a.M = int(M); a.N = MLP; a.K = D;
+    a.mode = EPI_BIAS_GELU; a.bias = P16(L.fc1_b);
+    if (int rc = gemm_bf16(a, stream)) return rc;
+    a = GemmArgs{};
+    a.A = mlp; a.lda = MLP; a.W = P16(L.fc2_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = MLP;
+    a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.fc2_b); a.gamma = P16(L.ls2); a.res = x;
+    if (int rc = gemm_bf16(a, stream)) return rc;
+  }
+
+  // ---- final norm, fused with the token slice of dino.py:25-30
+  int skip = 0, per = T;
+  switch (feature_type) {
+    case FP_FEATURE_ALL: skip = 0; per = T; break;
+    case FP_FEATURE_CLS: skip = 0; per = 1; break;
+    case FP_FEATURE_REG: skip = 1; per = NREG; break;
+    case FP_FEATURE_PATCH: skip = 1 + NREG; per = P; break;
+  }
+  return layernorm_bf16(x, reinterpret_cast<const bf16*>(w->norm_w), reinterpret_cast<const bf16*>(w->norm_b),
+                        reinterpret_cast<bf16*>(out), B * per, D, 1e-6f, T, skip, per, stream);
+}
+
+}  // namespace fp

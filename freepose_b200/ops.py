@@ -1,0 +1,225 @@
+"""Torch-tensor shims over the C ABI (one function per ``fp_*`` entry point).
+
+Every function enqueues on ``torch.cuda.current_stream()`` and returns device tensors; none of them
+synchronises and none has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (FP_EPI_BIAS, FP_EPI_BIAS_GELU, FP_EPI_BIAS_LS_RES, FP_EPI_PATCH_EMBED, KPAD, check, load, ptr,
+                   stream_ptr)
+
+bf16 = torch.bfloat16
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------- ViT stages
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int = FP_EPI_BIAS, *, gamma=None,
+         residual=None, out=None, pos=None, patches_per_img=0, tokens_per_img=0, token_offset=0):
+    """out = epilogue(a @ w.T); a (M,K) bf16, w (N,K) bf16.  See fp_gemm_bf16."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.dtype == bf16 and w.dtype == bf16 and w.shape[1] == K
+    if out is None:
+        out = residual if mode == FP_EPI_BIAS_LS_RES else torch.empty(M, N, dtype=bf16, device=a.device)
+    extra = residual if mode == FP_EPI_BIAS_LS_RES else pos
+    check(load().fp_gemm_bf16(ptr(a), a.stride(0), ptr(w), ptr(out), out.stride(0), M, N, K, mode, ptr(bias),
+                              ptr(gamma), ptr(extra), patches_per_img, tokens_per_img, token_offset,
+                              stream_ptr()), "fp_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6):
+    rows = x.numel() // 1024
+    out = torch.empty_like(x)
+    check(load().fp_layernorm_bf16(ptr(x), ptr(w), ptr(b), ptr(out), rows, eps, rows, 0, rows, stream_ptr()),
+          "fp_layernorm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int = 16, scale: float = 0.125):
+    assert qkv.dtype == bf16 and qkv.shape == (batch * tokens, 3 * heads * 64)
+    out = torch.empty(batch * tokens, heads * 64, dtype=bf16, device=qkv.device)
+    check(load().fp_attention_bf16(ptr(qkv), ptr(out), batch, tokens, heads, scale, stream_ptr()),
+          "fp_attention_bf16")
+    return out
+
+
+def im2col(image: torch.Tensor):
+    B, _, res, _ = image.shape
+    g = res // 14
+    out = torch.empty(B * g * g, KPAD, dtype=bf16, device=image.device)
+    is_f32 = image.dtype == torch.float32
+    assert is_f32 or image.dtype == bf16
+    check(load().fp_im2col_patches(ptr(image), int(is_f32), ptr(out), B, res, KPAD, stream_ptr()),
+          "fp_im2col_patches")
+    return out
+
+
+def normalize_image(image: torch.Tensor):
+    B, _, res, _ = image.shape
+    assert image.dtype == torch.float32
+    out = torch.empty(image.shape, dtype=bf16, device=image.device)
+    check(load().fp_normalize_image(ptr(image), ptr(out), B, res, stream_ptr()), "fp_normalize_image")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- score
+def score_topk(feats_t: torch.Tensor, feat_q: torch.Tensor, k: int = 3, weights=None, normalise_query=True,
+               return_patch_scores=False):
+    """Position-aligned per-patch cosine + mean + top-k (fp_score_topk).
+
+    feats_t (B,P,D) bf16, feat_q (P,D) or (1,P,D) bf16.  Returns (scores fp32 (B,), idx int32 (k,),
+    vals fp32 (k,), patch_scores or None).
+    """
+    B, P, D = feats_t.shape
+    feat_q = feat_q.reshape(P, D)
+    assert feats_t.dtype == bf16 and feat_q.dtype == bf16
+    dev = feats_t.device
+    lib = load()
+    ws = _ws(lib.fp_score_workspace_bytes(B, P, D), dev)
+    scores = torch.empty(B, dtype=torch.float32, device=dev)
+    idx = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+    patch = torch.empty(B, P, dtype=torch.float32, device=dev) if return_patch_scores else None
+    if weights is not None:
+        assert weights.dtype == torch.float32 and weights.shape == (B, P)
+    check(lib.fp_score_topk(ptr(feats_t), ptr(feat_q), ptr(weights), B, P, D, int(bool(normalise_query)),
+                            ptr(scores), ptr(patch), k, ptr(idx), ptr(vals), ptr(ws), ws.numel(), stream_ptr()),
+          "fp_score_topk")
+    return scores, idx[:k], vals[:k], patch
+
+
+def topk(scores: torch.Tensor, k: int):
+    B = scores.numel()
+    dev = scores.device
+    ws = _ws(B, dev)
+    idx = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+    check(load().fp_topk(ptr(scores), B, k, ptr(idx), ptr(vals), ptr(ws), ws.numel(), stream_ptr()), "fp_topk")
+    return idx[:k], vals[:k]
+
+
+def ffa_pool(feats: torch.Tensor, masks: torch.Tensor):
+    """feats (V,P,D) bf16, masks (V,res,res) bool/u8 -> (V,D) fp32, valid-count (V,) int32."""
+    V, P, D = feats.shape
+    res = masks.shape[-1]
+    m = masks.to(torch.uint8).contiguous()
+    out = torch.empty(V, D, dtype=torch.float32, device=feats.device)
+    valid = torch.empty(V, dtype=torch.int32, device=feats.device)
+    check(load().fp_ffa_pool(ptr(feats), ptr(m), V, res, D, ptr(out), ptr(valid), stream_ptr()), "fp_ffa_pool")
+    return out, valid
+
+
+# ------------------------------------------------------------------------------------------- raster
+@functools.lru_cache(maxsize=None)
+def _gamma_lut_host() -> np.ndarray:
+    i = np.arange(65536, dtype=np.float64) / 65535.0
+    return np.floor(255.0 * np.power(i, 1.0 / 2.2) + 0.5).astype(np.uint8)
+
+
+_gamma_lut_dev = {}
+
+
+def gamma_lut(device) -> torch.Tensor:
+    key = str(device)
+    if key not in _gamma_lut_dev:
+        _gamma_lut_dev[key] = torch.from_numpy(_gamma_lut_host()).to(device)
+    return _gamma_lut_dev[key]
+
+
+def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors: torch.Tensor, poses: torch.Tensor, fx, fy, cx, cy,
+              res: int, msaa: int = 4, cull_backfaces: bool = False):
+    """verts (V,3) fp32, faces (F,3) int32, colors (V,3) u8, poses (B,4,4)|(B,3,4) fp32 -> rgb u8 (B,res,res,3),
+    depth fp32 (B,res,res)."""
+    dev = verts.device
+    B = poses.shape[0]
+    p34 = poses[:, :3, :4].to(torch.float32).contiguous()
+    V, F = verts.shape[0], faces.shape[0]
+    assert verts.dtype == torch.float32 and faces.dtype == torch.int32 and colors.dtype == torch.uint8
+    lib = load()
+    nbytes = C.c_size_t(0)
+    check(lib.fp_raster_workspace_bytes(B, V, res, msaa, C.byref(nbytes)), "fp_raster_workspace_bytes")
+    ws = _ws(nbytes.value, dev)
+    rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
+    depth = torch.empty(B, res, res, dtype=torch.float32, device=dev)
+    args = _lib.RasterArgs(ptr(verts), ptr(faces), ptr(colors), V, F, ptr(p34), B, float(fx), float(fy), float(cx),
+                           float(cy), res, msaa, int(cull_backfaces), ptr(gamma_lut(dev)), ptr(rgb), ptr(depth))
+    check(lib.fp_rasterize(C.byref(args), ptr(ws), ws.numel(), stream_ptr()), "fp_rasterize")
+    return rgb, depth
+
+
+# ------------------------------------------------------------------------------------------- geometry
+def mask_bbox(depth: torch.Tensor, fallback=(105, 315), min_count: int = 100, return_mask: bool = False):
+    B, res, _ = depth.shape
+    dev = depth.device
+    bbox = torch.empty(B, 4, dtype=torch.int32, device=dev)
+    count = torch.empty(B, dtype=torch.int32, device=dev)
+    mask = torch.empty(B, res, res, dtype=torch.uint8, device=dev) if return_mask else None
+    check(load().fp_mask_bbox(ptr(depth), B, res, int(fallback[0]), int(fallback[1]), min_count, ptr(bbox),
+                              ptr(count), ptr(mask), stream_ptr()), "fp_mask_bbox")
+    return bbox, count, mask
+
+
+@functools.lru_cache(maxsize=None)
+def _norm_lut_host() -> torch.Tensor:
+    """Normalize(bf16(v/255)) per channel, computed with the reference's own torch ops (dino.py:12,16 on a
+    bf16 tensor; the /255 and .float() of renderer.py:121)."""
+    v = torch.from_numpy(np.arange(256) / 255).float().to(bf16)               # (256,)
+    mean = torch.as_tensor((0.485, 0.456, 0.406), dtype=bf16).view(3, 1)
+    std = torch.as_tensor((0.229, 0.224, 0.225), dtype=bf16).view(3, 1)
+    x = v.view(1, 256).repeat(3, 1)
+    return x.sub_(mean).div_(std).contiguous()                                   # (3,256) bf16
+
+
+_norm_lut_dev = {}
+
+
+def norm_lut(device) -> torch.Tensor:
+    key = str(device)
+    if key not in _norm_lut_dev:
+        _norm_lut_dev[key] = _norm_lut_host().to(device)
+    return _norm_lut_dev[key]
+
+
+def crop_resize_pad(src: torch.Tensor, boxes: torch.Tensor, target: int, to_patches: bool = False):
+    """CropResizePad gather.  src: u8 (B,H,W,3) or fp32 (B,3,H,W); boxes (B,4) int32 xyxy (exclusive)."""
+    dev = src.device
+    B = src.shape[0]
+    u8 = src.dtype == torch.uint8
+    H, W = (src.shape[1], src.shape[2]) if u8 else (src.shape[2], src.shape[3])
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if to_patches:
+        g = target // 14
+        dst = torch.empty(B * g * g, KPAD, dtype=bf16, device=dev)
+    else:
+        dst = torch.empty(B, 3, target, target, dtype=torch.float32, device=dev)
+    boxes = boxes.to(torch.int32).contiguous()
+    check(load().fp_crop_resize_pad(ptr(src), int(u8), ptr(boxes), ptr(norm_lut(dev)), ptr(dst), int(to_patches), B,
+                                    H, W, target, KPAD, ptr(status), stream_ptr()), "fp_crop_resize_pad")
+    return dst, status
+
+
+def depth_extents(depth: torch.Tensor, K, view_idx=None):
+    """(n,8) fp64: xmin,xmax,ymin,ymax,sum_x,sum_y,sum_z,count of K^-1 [u v 1]^T d over non-zero points."""
+    B, res, _ = depth.shape
+    dev = depth.device
+    kinv = torch.from_numpy(np.linalg.inv(np.asarray(K))).to(torch.float64).reshape(9).to(dev)
+    if view_idx is not None:
+        view_idx = view_idx.to(torch.int32).contiguous()
+        n = view_idx.numel()
+    else:
+        n = B
+    out = torch.empty(n, 8, dtype=torch.float64, device=dev)
+    check(load().fp_depth_extents(ptr(depth), ptr(view_idx), n, res, ptr(kinv), ptr(out), stream_ptr()),
+          "fp_depth_extents")
+    return out

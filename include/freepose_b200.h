@@ -1,0 +1,172 @@
+/* freepose_b200 -- C ABI of the B200 (sm_100a) render-and-compare pose engine.
+ *
+ * Drop-in boundary for FreePose's per-proposal hot path.  The reference has no FFI of its own for this
+ * path: its boundary is the Python surface of src/pipeline.  Every entry point below
+ * therefore names the reference Python lines whose arithmetic it replaces; the ctypes binding a maintainer
+ * adds is shown in INTEGRATION.md and implemented in freepose_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless marked "host";
+ *   - buffers are borrowed for the duration of the call, never retained; no hidden allocations: callers
+ *     pass workspaces sized by the matching *_workspace_bytes();
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return 0 on success, negative on error (-1 argument/contract violation, -2 CUDA error);
+ *     fp_last_error() returns the message for the calling thread;
+ *   - bf16 tensors are raw uint16 bit patterns (torch.bfloat16 storage).
+ */
+#ifndef FREEPOSE_B200_H_
+#define FREEPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FP_API __attribute__((visibility("default")))
+#else
+#define FP_API
+#endif
+
+#define FP_ABI_VERSION 1
+
+FP_API int fp_abi_version(void);
+FP_API const char* fp_last_error(void);
+FP_API int fp_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * DINOv2 ViT-L/14-reg feature extractor
+ * replaces: src/pipeline/retrieval/dino.py:14-32  (DINOv2FeatureExtractor.forward:
+ *           Normalize -> prepare_tokens_with_masks -> blocks[:layer] -> norm -> token slice)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct fp_vit_layer {          /* all bf16; nn.Linear weights are [out, in] row-major        */
+  const void *ln1_w, *ln1_b;           /* [1024]                                                     */
+  const void *qkv_w, *qkv_b;           /* [3072, 1024], [3072]                                       */
+  const void *proj_w, *proj_b;         /* [1024, 1024], [1024]                                       */
+  const void *ls1;                     /* [1024] LayerScale gamma                                    */
+  const void *ln2_w, *ln2_b;
+  const void *fc1_w, *fc1_b;           /* [4096, 1024], [4096]                                       */
+  const void *fc2_w, *fc2_b;           /* [1024, 4096], [1024]                                       */
+  const void *ls2;
+} fp_vit_layer;
+
+typedef struct fp_vit_weights {
+  int depth;                           /* number of entries in `layers` (24 for the full checkpoint) */
+  const fp_vit_layer* layers;          /* HOST array of `depth` structs holding device pointers      */
+  const void* patch_w;                 /* [1024, 640] bf16: conv weight (1024,3,14,14) flattened to
+                                          588 columns (c*196 + ky*14 + kx) and zero padded to 640    */
+  const void* patch_b;                 /* [1024]                                                     */
+  const void* norm_w;                  /* [1024] final LayerNorm                                     */
+  const void* norm_b;
+  int pos_res;                         /* crop resolution the two tensors below were prepared for    */
+  const void* pos_embed;               /* [1 + g*g, 1024] bf16: bicubic(antialias) resampled
+                                          pos_embed for g = pos_res/14 (row 0 = cls position)        */
+  const void* special_tokens;          /* [5, 1024] bf16: row 0 = bf16(cls_token + pos_embed[0]),
+                                          rows 1..4 = register tokens                                */
+} fp_vit_weights;
+
+enum { FP_INPUT_IMAGE_F32 = 0,   /* (B,3,res,res) fp32 in [0,1]; bf16 Normalize applied (dino.py:12,16) */
+       FP_INPUT_IMAGE_BF16 = 1,  /* (B,3,res,res) bf16, already normalised                              */
+       FP_INPUT_PATCHES = 2 };   /* [B*g*g, 640] bf16 normalised patch matrix (fp_crop_resize_pad)      */
+
+enum { FP_FEATURE_ALL = 0,       /* (B, 1+4+g*g, 1024)                                                  */
+       FP_FEATURE_CLS = 1,       /* (B, 1024)        dino.py:25-26                                      */
+       FP_FEATURE_REG = 2,       /* (B, 4, 1024)     dino.py:27-28                                      */
+       FP_FEATURE_PATCH = 3 };   /* (B, g*g, 1024)   dino.py:29-30                                      */
+
+FP_API size_t fp_vit_workspace_bytes(int batch, int res);
+FP_API int fp_vit_forward(const fp_vit_weights* weights /* host struct */, const void* input, int input_kind,
+                          int batch, int res, int layer, int feature_type, void* out_tokens_bf16,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage-level entry points (same kernels; used by the per-stage parity tests and by fp_vit_forward). */
+enum { FP_EPI_BIAS = 0, FP_EPI_BIAS_GELU = 1, FP_EPI_BIAS_LS_RES = 2, FP_EPI_PATCH_EMBED = 3 };
+/* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, fp32 accumulate.  replaces nn.Linear (+GELU /
+ * +LayerScale+residual) inside the hub Block and the patch-embed conv (dino.py:16-21). */
+FP_API int fp_gemm_bf16(const void* A, int lda, const void* W, void* out, int ldo, int M, int N, int K, int mode,
+                        const void* bias, const void* gamma, const void* residual_or_pos, int patches_per_img,
+                        int tokens_per_img, int token_offset, void* stream);
+/* rows of 1024: y = bf16(((x-mean)*rstd)*w + b); replaces nn.LayerNorm(eps=1e-6) in the hub Block / norm */
+FP_API int fp_layernorm_bf16(const void* x, const void* w, const void* b, void* out, int rows, float eps,
+                             int in_group_stride, int in_skip, int rows_per_group, void* stream);
+/* qkv [B*T, 3072] -> out [B*T, 1024]; replaces the hub (Mem-Eff)Attention core, 16 heads x 64 */
+FP_API int fp_attention_bf16(const void* qkv, void* out, int batch, int tokens, int heads, float scale,
+                             void* stream);
+FP_API int fp_im2col_patches(const void* image, int src_is_f32, void* patches_bf16, int batch, int res, int kpad,
+                             void* stream);
+/* replaces torchvision T.Normalize on the bf16 image (dino.py:12,16) */
+FP_API int fp_normalize_image(const float* image, void* out_bf16, int batch, int res, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Score + top-k
+ * replaces: src/pipeline/estimators/pose_estimator.py:85-92   (normalize, einsum, mean, topk(3))
+ *           src/pipeline/estimators/online_pose_estimator.py:68-79 (incl. mask_scores weighting, max/argmax)
+ * feats_t (B,P,D) bf16 template tokens, feat_q (P,D) bf16 query tokens, weights (B,P) fp32 or NULL.
+ * scores_out (B) fp32: bf16-rounded mean as float (weights NULL) or the fp32 weighted mean.
+ * patch_scores_out (B,P) fp32 or NULL.  top-k: descending, ties -> lowest index.
+ * ------------------------------------------------------------------------------------------------ */
+FP_API size_t fp_score_workspace_bytes(int B, int P, int D);
+FP_API int fp_score_topk(const void* feats_t, const void* feat_q, const float* weights, int B, int P, int D,
+                         int normalise_query, float* scores_out, float* patch_scores_out, int k,
+                         int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* top-k over an fp32 score vector already on the device (e.g. after the multi-GPU all-gather) */
+FP_API int fp_topk(const float* scores, int B, int k, int32_t* topk_idx, float* topk_val, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* replaces: scripts/extract_retrieval_features.py:49-57 (FFA: masked mean of patch tokens).
+ * masks (V,res,res) u8, feats (V,g*g,D) bf16 -> out (V,D) fp32, valid (V) int32 = selected patch count */
+FP_API int fp_ffa_pool(const void* feats, const uint8_t* masks, int V, int res, int D, float* out, int32_t* valid,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasteriser
+ * replaces: src/pipeline/retrieval/renderer.py:43-95 (MeshRenderer.render / render_from_poses: one pyrender
+ *           GL draw + glReadPixels per pose)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct fp_raster_args {
+  const float* verts;       /* [V,3] fp32 mesh vertices (object frame, already at rendering scale)      */
+  const int32_t* faces;     /* [F,3]                                                                     */
+  const uint8_t* colors;    /* [V,3] u8 vertex colours                                                   */
+  int V, F;
+  const float* poses;       /* [B,12] row-major 3x4 object->camera (OpenCV frame), rows of the 4x4 pose  */
+  int B;
+  float fx, fy, cx, cy;     /* pyrender.IntrinsicsCamera(fx, fy, cx, cy), renderer.py:37                 */
+  int res;
+  int msaa;                 /* 4 = pyrender's multisampled offscreen target, 1 = centre sampling         */
+  int cull_backfaces;       /* 0 = RenderFlags.SKIP_CULL_FACES (reference default, renderer.py:63-66)    */
+  const uint8_t* gamma_lut; /* [65536] u8: round(255 * (i/65535)^(1/2.2))                                */
+  uint8_t* rgb;             /* out [B,res,res,3] u8                                                      */
+  float* depth;             /* out [B,res,res] fp32 metres, 0 = background                               */
+} fp_raster_args;
+FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes /* host out */);
+FP_API int fp_rasterize(const fp_raster_args* args /* host struct */, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry around the renders
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: renderer.py:98-117 (mask = depth > 0; < min_count px -> mask[lo:hi, lo:hi] = True; mask_to_bbox).
+ * bbox_out (B,4) int32 xmin,ymin,xmax,ymax; count_out (B) or NULL; mask_out (B,res,res) u8 or NULL */
+FP_API int fp_mask_bbox(const float* depth, int B, int res, int fallback_lo, int fallback_hi, int min_count,
+                        int32_t* bbox_out, int32_t* count_out, uint8_t* mask_out, void* stream);
+/* replaces: src/utils/bbox_utils.py:20-56 (CropResizePad.__call__) fused with renderer.py:119-129 and, for the
+ * patch-matrix output, with dino.py:12,16 (Normalize) and the patch-embed im2col.
+ * boxes (B,4) int32 x1,y1,x2,y2 already extended/clamped (slice semantics: x2,y2 exclusive).
+ * src: u8 HWC (B,src_h,src_w,3) or fp32 CHW (B,3,src_h,src_w).  dst: fp32 CHW (B,3,T,T) or the bf16 patch
+ * matrix [B*(T/14)^2, kpad] (needs norm_lut [3*256] bf16 = Normalize(bf16(v/255)) per channel).
+ * status: int32 device word, set to 1+index of a box the reference would have failed on (else untouched). */
+FP_API int fp_crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, const void* norm_lut,
+                              void* dst, int dst_is_patches, int B, int src_h, int src_w, int T, int kpad,
+                              int32_t* status, void* stream);
+/* replaces: src/pipeline/utils.py:122-145 (depthmap_to_pointcloud) reduced to what utils.py:148-170
+ * (get_z_from_pointcloud) and pose_estimator.py:103-111 consume.  view_idx (n) int32 or NULL selects views;
+ * kinv (9) fp64 device = inv(K) row-major; out (n,8) fp64: xmin,xmax,ymin,ymax,sum_x,sum_y,sum_z,count */
+FP_API int fp_depth_extents(const float* depth, const int32_t* view_idx, int n, int res, const double* kinv,
+                            double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREEPOSE_B200_H_ */
