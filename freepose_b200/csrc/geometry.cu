@@ -93,8 +93,8 @@ __device__ inline CropParams crop_params(int x1, int y1, int x2, int y2, int T) 
   c.ok = (c.w0 > 0 && c.h0 > 0);
   if (!c.ok) { c.w1 = c.h1 = c.pad_left = c.pad_top = c.padded = c.s2 = 0; c.inv1 = c.inv2 = 0.f; return c; }
   const int m = max(c.w0, c.h0);
-  // scale_factor = target_max / max(box_sizes): Python int / int64 tensor -> float32 true division
-  const float scale32 = __fdiv_rn(float(T), float(m));
+  // scale_factor = target_max / max(box_sizes): Tensor.__rtruediv__ = reciprocal(tensor) * scalar in float32
+  const float scale32 = __fmul_rn(__frcp_rn(float(m)), float(T));
   const double s = double(scale32);                    // scale.item()
   c.h1 = int(floor(double(c.h0) * s));                 // F.interpolate output size
   c.w1 = int(floor(double(c.w0) * s));

@@ -1,0 +1,86 @@
+"""Drop-in for reference ``src/pipeline/estimators/online_pose_estimator.py:16-95`` (coarse -> fine)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ..utils import as_mesh, rescaled_extents, tco_from_extents
+from .pose_estimator import DinoPoseEstimator
+
+
+def _rotvec_angle(R: np.ndarray) -> np.ndarray:
+    """|rotation vector| of a batch of rotation matrices = geodesic angle (what the reference obtains through
+    scipy ``Rotation.from_matrix(diffs).as_rotvec()`` + norm, online_pose_estimator.py:30)."""
+    tr = np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0)
+    s = 0.5 * np.sqrt((R[:, 2, 1] - R[:, 1, 2]) ** 2 + (R[:, 0, 2] - R[:, 2, 0]) ** 2 + (R[:, 1, 0] - R[:, 0, 1]) ** 2)
+    return np.arctan2(s, tr)
+
+
+class DinoOnlinePoseEstimator(nn.Module):
+    def __init__(self, n_coarse_poses=600, n_fine_poses=10000, cache_size=50, save_all=False,
+                 cache_dir="./data/cache", resolution=420, **extractor_kwargs):
+        super().__init__()
+        self.coarse_estimator = DinoPoseEstimator(n_coarse_poses, cache_size, save_all, cache_dir,
+                                                  resolution=resolution, **extractor_kwargs)
+        self.feature_extractor = self.coarse_estimator.feature_extractor  # one set of weights in HBM, not two
+        self.fine_mesh_poses = np.array(self.coarse_estimator.generate_poses(n_fine_poses))
+        self.renderer = self.coarse_estimator.renderer
+        self.rendering_scale = 0.25
+        self.device = self.coarse_estimator.device
+
+    def to(self, *args, **kwargs):
+        return self
+
+    @staticmethod
+    def geodesic_distance(render_poses, query_pose, degrees=True):
+        diffs = render_poses[:, :3, :3] @ query_pose[:3, :3].T
+        d = _rotvec_angle(diffs)
+        return np.rad2deg(d) if degrees else d
+
+    def forward(self, proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose=None,
+                neighborhood=15, layer=22, batch_size=128, mask_scores=False):
+        if prev_pose is None:
+            coarse = self.coarse_estimator.forward(proposal, template_dict, K, bbox, est_scale, layer, batch_size,
+                                                   return_query_feat=True)
+            query_feat = coarse["query_feat"]  # NOT normalised -- reference quirk kept (online_pose_estimator.py:41,50)
+            prev_pose = coarse["TCO"][0]
+        else:
+            query_feat = None
+        return self.forward_fine(proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose,
+                                 neighborhood, layer, mask_scores, query_feat)
+
+    @torch.inference_mode()
+    def forward_fine(self, proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose,
+                     neighborhood=15, layer=22, mask_scores=False, query_feat=None):
+        normalise_query = query_feat is None
+        if query_feat is None:
+            query_feat = self.feature_extractor(proposal[None], layer=layer, feature_type="patch")
+        dists = self.geodesic_distance(self.fine_mesh_poses, np.asarray(prev_pose))
+        close = np.where(dists < neighborhood)[0]
+        if close.size == 0:
+            raise ValueError("no fine pose within the neighbourhood of prev_pose")
+        selected = self.fine_mesh_poses[close]
+        m = as_mesh(mesh).copy().apply_scale(self.rendering_scale)  # the reference scales in place and back
+        rgb, depth = self.renderer.render_device(m, selected)
+        T = self.renderer.resolution
+        patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
+        feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+        weights = None
+        if mask_scores:
+            g = T // 14
+            pm = torch.as_tensor(proposal_mask).to(self.device).bool()
+            mk = torch.logical_or(masks.bool(), pm[None]).float()
+            weights = F.interpolate(mk[None], size=(g, g), mode="bilinear")[0].reshape(len(close), g * g).contiguous()
+        scores, top_idx, top_val, _ = ops.score_topk(feats, query_feat, k=1, weights=weights,
+                                                     normalise_query=normalise_query)
+        top_index = int(top_idx.item())
+        K_t = np.asarray(template_dict["intrinsic"]) if template_dict is not None else \
+            np.array([[self.renderer.focal, 0, T / 2], [0, self.renderer.focal, T / 2], [0, 0, 1]])
+        ext = ops.depth_extents(depth, K_t, view_idx=top_idx).cpu().numpy()
+        dx, dy = rescaled_extents(ext[0], est_scale, recentre=False)
+        TCO = tco_from_extents(bbox, dx, dy, K, selected[top_index])
+        return {"TCO": [TCO], "scores": [top_val[0].float().cpu().numpy()], "proposal": proposal, "K": K,
+                "bbox": bbox, "all_scores": scores, "selected_poses": selected}

@@ -1,0 +1,149 @@
+"""Drop-in for reference ``src/pipeline/estimators/pose_estimator.py:18-147`` on the B200 engine.
+
+``forward`` keeps the reference contract (pre-rendered ``template_dict``).  ``forward_mesh`` is the
+B200-native hot path named by the north star: hypotheses are rasterised on the device, cropped into the
+patch matrix, pushed through the ViT and scored without leaving HBM.
+"""
+from __future__ import annotations
+
+import shutil
+from collections import OrderedDict
+from fcntl import LOCK_EX, LOCK_UN, flock
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..retrieval.dino import DINOv2FeatureExtractor
+from ..retrieval.renderer import MeshRenderer
+from ..utils import generate_poses, rescaled_extents, tco_from_extents
+
+bf16 = torch.bfloat16
+
+
+class DinoPoseEstimator(nn.Module):
+    def __init__(self, n_poses=600, cache_size=50, save_all=False, cache_dir="./data/cache", feature_extractor=None,
+                 resolution=420, **extractor_kwargs):
+        super().__init__()
+        self.feature_extractor = feature_extractor or DINOv2FeatureExtractor(**extractor_kwargs)
+        self.device = self.feature_extractor.engine.device
+        self.mesh_poses = self.generate_poses(n_poses)
+        self.feature_cache = OrderedDict()  # model_name -> (n_views, P, 1024) bf16, device resident
+        self.cache_size = cache_size
+        self.save_all = save_all
+        self.cache_dir = Path(cache_dir)
+        self.cache_dir.mkdir(parents=True, exist_ok=True)
+        self.renderer = MeshRenderer(n_poses, resolution=resolution, device=self.device)
+
+    def to(self, *args, **kwargs):  # parameters already live on the device in bf16
+        return self
+
+    generate_poses = staticmethod(generate_poses)
+
+    # ---------------------------------------------------------------- features + cache (pose_estimator.py:31-74)
+    def _extract_features(self, proposals, layer=22, batch_size=128):
+        n = len(proposals)
+        P = (proposals.shape[-1] // 14) ** 2
+        feats = torch.empty(n, P, 1024, dtype=bf16, device=self.device)
+        for i in range(0, n, batch_size):
+            chunk = proposals[i:i + batch_size].to(self.device, non_blocking=True)
+            self.feature_extractor.engine.forward(chunk.float(), layer=layer, feature_type="patch",
+                                                  out=feats[i:i + batch_size])
+        return feats
+
+    def _cache_features(self, key, features):
+        self.feature_cache[key] = features
+        self.feature_cache.move_to_end(key)
+        cache_path = self.cache_dir / f"{key}.pth"
+        if self.save_all and not cache_path.exists():
+            with open(cache_path, "wb") as f:
+                flock(f, LOCK_EX)
+                torch.save(features.cpu(), f)
+                flock(f, LOCK_UN)
+        if len(self.feature_cache) > self.cache_size:
+            oldest_key, oldest = self.feature_cache.popitem(last=False)
+            torch.save(oldest.cpu(), self.cache_dir / f"{oldest_key}.pth")
+
+    def _get_template_features(self, template_dict, layer=22, batch_size=128):
+        name = template_dict["model_name"]
+        if name in self.feature_cache:
+            self.feature_cache.move_to_end(name)
+            return self.feature_cache[name]
+        cache_path = self.cache_dir / f"{name}.pth"
+        if cache_path.exists():
+            feats = torch.load(cache_path).to(self.device, dtype=bf16)
+        else:
+            feats = self._extract_features(template_dict["templates"], layer=layer, batch_size=batch_size)
+        self._cache_features(name, feats)
+        return feats
+
+    def __del__(self):
+        try:
+            shutil.rmtree(self.cache_dir)
+        except Exception:  # noqa: BLE001 -- interpreter shutdown / already removed
+            pass
+
+    # ---------------------------------------------------------------- reference contract
+    @torch.inference_mode()
+    def forward(self, proposal, template_dict, K, bbox, est_scale, layer=22, batch_size=128,
+                return_query_feat=False):
+        if self.cache_size > 0:
+            feats_template = self._get_template_features(template_dict, layer=layer, batch_size=batch_size)
+        else:
+            feats_template = self._extract_features(template_dict["templates"], layer=layer, batch_size=batch_size)
+        query_feat = self.feature_extractor(proposal[None], layer=layer, feature_type="patch")
+        scores, top_idx, top_val, _ = ops.score_topk(feats_template, query_feat, k=3)
+        top_indices = top_idx.cpu().numpy().astype(np.int64)
+        out_dict = {
+            "TCO": [],
+            "scores": top_val.cpu().numpy().astype(np.float32),
+            "proposal": proposal,
+            "K": K,
+            "bbox": bbox,
+            "retrieved_proposals": [template_dict["templates"][idx] for idx in top_indices],
+            "all_scores": scores,  # needed by dino_inference_video --no_rescore (absent in the reference: KeyError)
+            "top_indices": top_indices,
+        }
+        depths = template_dict["depths"]
+        sel = torch.stack([torch.as_tensor(depths[int(i)]) for i in top_indices]).to(self.device, torch.float32)
+        K_t = np.asarray(template_dict["intrinsic"])
+        ext = ops.depth_extents(sel.contiguous(), K_t).cpu().numpy()
+        bbox_np = np.asarray(bbox, dtype=np.float64) if not torch.is_tensor(bbox) else bbox
+        for j, idx in enumerate(top_indices):
+            dx, dy = rescaled_extents(ext[j], est_scale, recentre=True)
+            out_dict["TCO"].append(tco_from_extents(bbox_np, dx, dy, K, self.mesh_poses[idx]))
+        if return_query_feat:
+            out_dict["query_feat"] = query_feat
+        return out_dict
+
+    # ---------------------------------------------------------------- B200-native hot path
+    @torch.inference_mode()
+    def render_features(self, mesh, poses=None, layer=22, resolution=None):
+        """raster -> mask bbox -> CropResizePad -> patch matrix -> ViT.  Returns (feats (B,P,1024) bf16,
+        depth (B,res,res) fp32, crop status)."""
+        rgb, depth = self.renderer.render_device(mesh, poses)
+        T = resolution or self.renderer.resolution
+        patches, _, _, status = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
+        feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+        return feats, depth, status
+
+    @torch.inference_mode()
+    def forward_mesh(self, proposal, mesh, K, bbox, est_scale, layer=22, poses=None, k=3):
+        """Render-and-compare of one proposal against all hypotheses of `mesh` (already at rendering scale).
+        Same outputs as ``forward`` (without 'retrieved_proposals')."""
+        pose_list = self.mesh_poses if poses is None else list(poses)
+        feats, depth, _ = self.render_features(mesh, poses, layer=layer)
+        query_feat = self.feature_extractor(proposal[None], layer=layer, feature_type="patch")
+        scores, top_idx, top_val, _ = ops.score_topk(feats, query_feat, k=k)
+        r = self.renderer.resolution
+        K_t = np.array([[self.renderer.focal, 0, r / 2], [0, self.renderer.focal, r / 2], [0, 0, 1]])
+        ext = ops.depth_extents(depth, K_t, view_idx=top_idx).cpu().numpy()
+        top_indices = top_idx.cpu().numpy().astype(np.int64)
+        out = {"TCO": [], "scores": top_val.cpu().numpy().astype(np.float32), "proposal": proposal, "K": K,
+               "bbox": bbox, "all_scores": scores, "top_indices": top_indices}
+        for j, idx in enumerate(top_indices):
+            dx, dy = rescaled_extents(ext[j], est_scale, recentre=True)
+            out["TCO"].append(tco_from_extents(bbox, dx, dy, K, pose_list[idx]))
+        return out

@@ -1,0 +1,50 @@
+"""ORACLE (test infrastructure): ctypes wrapper of oracle/raster_ref.c (see its header for scope and the
+"parity unpinned" note for row R)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+_SO = _DIR / "_build" / "libraster_ref.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src = _DIR / "raster_ref.c"
+    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        _SO.parent.mkdir(exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", str(src), "-o",
+                        str(_SO), "-lm"], check=True)
+    return _SO
+
+
+def gamma_lut() -> np.ndarray:
+    i = np.arange(65536, dtype=np.float64) / 65535.0
+    return np.floor(255.0 * np.power(i, 1.0 / 2.2) + 0.5).astype(np.uint8)
+
+
+def render(verts, faces, colors, poses, fx, fy, cx, cy, res, msaa=4, cull=False):
+    """verts (V,3), faces (F,3), colors (V,3) u8, poses (B,4,4) -> rgb u8 (B,res,res,3), depth f32 (B,res,res)."""
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+        _lib.raster_ref.restype = C.c_int
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    faces = np.ascontiguousarray(faces, dtype=np.int32)
+    colors = np.ascontiguousarray(colors, dtype=np.uint8)
+    p = np.ascontiguousarray(np.asarray(poses, dtype=np.float32)[:, :3, :4])
+    B = p.shape[0]
+    lut = gamma_lut()
+    rgb = np.zeros((B, res, res, 3), dtype=np.uint8)
+    depth = np.zeros((B, res, res), dtype=np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _lib.raster_ref(vp(verts), vp(faces), vp(colors), C.c_int(verts.shape[0]), C.c_int(faces.shape[0]), vp(p),
+                         C.c_int(B), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_int(res),
+                         C.c_int(msaa), C.c_int(int(cull)), vp(lut), vp(rgb), vp(depth))
+    if rc != 0:
+        raise RuntimeError(f"raster_ref failed: {rc}")
+    return rgb, depth

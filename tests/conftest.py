@@ -1,0 +1,37 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    d = ROOT / "tests" / "golden"
+    return {p.stem: np.load(p, allow_pickle=False) for p in d.glob("*.npz")}
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """Build (if needed) and load the C-ABI library -- builds on the CPU box, prebuilt on the GPU box."""
+    from freepose_b200 import _lib, build
+    build.build()
+    return _lib.load()

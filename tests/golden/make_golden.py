@@ -1,0 +1,147 @@
+"""Mints tests/golden/*.npz by running the REFERENCE'S OWN CODE (imported unmodified from /root/reference via
+oracle/refimport.py) on seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The fixtures travel with the repository; tests compare the oracle restatements (and, on the GPU, the CUDA
+kernels) against them.  Nothing at test time reads /root/reference.
+"""
+from __future__ import annotations
+
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import refimport  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def golden_poses():
+    pe = refimport.import_reference("src.pipeline.estimators.pose_estimator")
+    gen = pe.DinoPoseEstimator.generate_poses
+    p42 = np.array(gen(42))
+    p600 = np.array(gen(600))
+    p20k = np.array(gen(20000))
+    np.savez_compressed(OUT / "poses.npz", p42=p42, p600_first8=p600[:8], p600_last8=p600[-8:],
+                        p600_sha=sha(p600), p20000_sha=sha(p20k), p20000_rows=p20k[[0, 1, 7777, 19999]])
+
+
+def golden_geometry():
+    ru = refimport.import_reference("src.pipeline.utils")
+    rng = np.random.default_rng(7)
+    cases = []
+    K_t = np.array([[600, 0, 210], [0, 600, 210], [0, 0, 1]])
+    for i in range(4):
+        res = 420 if i % 2 == 0 else 224
+        Kt = K_t if res == 420 else np.array([[320.0, 0, 112], [0, 320.0, 112], [0, 0, 1]])
+        d = np.zeros((res, res), np.float32)
+        y0, x0 = rng.integers(10, res // 3, 2)
+        h, w = rng.integers(res // 4, res // 2, 2)
+        d[y0:y0 + h, x0:x0 + w] = rng.uniform(0.85, 1.35, (h, w)).astype(np.float32)
+        d[rng.random((res, res)) < 0.3] = 0
+        bbox = np.array([100.0 + i, 80.0, 300.0, 260.0 + 2 * i])
+        Kq = np.array([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
+        T0 = np.eye(4); T0[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]; T0[2, 3] = 1.1
+        est_scale = float(rng.uniform(0.05, 0.6))
+        pc = ru.depthmap_to_pointcloud(d, Kt)
+        # coarse rescaling, pose_estimator.py:104-111
+        pcc = pc.copy(); m = pcc.mean(axis=0); pcc -= m; pcc /= 0.25; pcc *= est_scale; pcc += m
+        tco_coarse = ru.get_z_from_pointcloud(bbox, pcc, Kq, T0)
+        # fine rescaling, online_pose_estimator.py:82-86
+        pcf = pc.copy(); pcf /= 0.25; pcf *= est_scale
+        tco_fine = ru.get_z_from_pointcloud(bbox, pcf, Kq, T0)
+        cases.append(dict(depth=d, Kt=Kt, bbox=bbox, Kq=Kq, T0=T0, est_scale=est_scale, n_points=pc.shape[0],
+                          pc_sha=sha(pc), tco_coarse=tco_coarse, tco_fine=tco_fine,
+                          bbox_of_mask=ru.mask_to_bbox(d > 0)))
+    np.savez_compressed(OUT / "geometry.npz", **{f"c{i}_{k}": v for i, c in enumerate(cases) for k, v in c.items()})
+
+
+def golden_crop():
+    bu = refimport.import_reference("src.utils.bbox_utils")
+    rng = np.random.default_rng(11)
+    store = {}
+    # (H, W, T, bbox_extend, boxes): small full-output cases + large checksum cases
+    specs = [
+        (60, 90, 84, 0, [[5, 7, 50, 40], [10, 10, 40, 40], [0, 0, 90, 60]]),
+        (60, 90, 84, 0.2, [[5, 7, 50, 40], [30, 20, 88, 58], [12, 3, 31, 57]]),
+        (420, 420, 420, 0, [[100, 120, 330, 344], [150, 100, 287, 390], [105, 105, 314, 314]]),
+        (420, 420, 224, 0, [[100, 120, 330, 344], [50, 60, 380, 200], [0, 0, 419, 419]]),
+        (480, 640, 420, 0.2, [[345, 136, 575, 360], [274, 255, 498, 479], [10, 20, 600, 300]]),
+        (480, 640, 224, 0.2, [[317, 4, 617, 272], [0, 0, 100, 470], [500, 400, 639, 479]]),
+    ]
+    for i, (H, W, T, ext, boxes) in enumerate(specs):
+        imgs = rng.random((len(boxes), 3, H, W)).astype(np.float32)
+        boxes = np.array(boxes, dtype=np.int64)
+        out = bu.CropResizePad(T, (H, W), bbox_extend=ext)(torch.from_numpy(imgs), torch.from_numpy(boxes)).numpy()
+        store[f"c{i}_spec"] = np.array([H, W, T], dtype=np.int64)
+        store[f"c{i}_ext"] = np.float64(ext)
+        store[f"c{i}_boxes"] = boxes
+        store[f"c{i}_seed_imgs_sha"] = sha(imgs)
+        store[f"c{i}_out_sha"] = sha(out)
+        if H * W < 10000:
+            store[f"c{i}_imgs"] = imgs
+            store[f"c{i}_out"] = out
+    store["rng_seed"] = np.int64(11)
+    np.savez_compressed(OUT / "crop.npz", **store)
+
+
+def golden_dino_forward():
+    """The reference's DINOv2FeatureExtractor.forward (dino.py:14-32), unmodified, around the hub-shaped oracle
+    ViT (2 synthetic blocks, 56 px crops) in fp32: pins Normalize + prepare_tokens + block loop + norm + slices."""
+    from freepose_b200.vit_weights import synthetic_state_dict
+    from oracle.vit import OracleViT
+    sd = synthetic_state_dict(seed=3, depth=2)
+    fe = refimport.reference_feature_extractor(OracleViT(sd).float())
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(2, 3, 56, 56, generator=g)
+    out = {"imgs": imgs.numpy()}
+    for ft in ("cls", "reg", "patch"):
+        for layer in (1, 2):
+            out[f"{ft}_{layer}"] = fe(imgs, layer=layer, feature_type=ft).numpy()
+    np.savez_compressed(OUT / "dino_forward.npz", **out)
+
+
+def golden_score():
+    """The reference's scoring expression (pose_estimator.py:85-90 / online_pose_estimator.py:68-79) evaluated
+    verbatim with einops on CPU bf16 tensors."""
+    import torch.nn.functional as F
+    from einops import einsum
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(1, 9, 1024, generator=g)
+    t = (0.6 * q + 0.8 * torch.randn(12, 9, 1024, generator=g))
+    t[3] = t[5]  # exact tie
+    feats_template, query_feat = t.to(torch.bfloat16), q.to(torch.bfloat16)
+    signature = "b n d, b n d -> b n"
+    scores = einsum(F.normalize(feats_template, dim=-1), F.normalize(query_feat, dim=-1), signature).mean(dim=-1)
+    top_scores, top_indices = torch.topk(scores, 3)
+    masks = torch.rand(12, 9, generator=g)
+    qn = F.normalize(query_feat, dim=-1)
+    s_fine = einsum(qn, F.normalize(feats_template, dim=-1), signature)
+    weighted = (s_fine * masks).sum(dim=-1) / masks.sum(dim=-1)
+    np.savez_compressed(OUT / "score.npz", feats_t=feats_template.view(torch.int16).numpy(),
+                        feat_q=query_feat.view(torch.int16).numpy(), scores=scores.float().numpy(),
+                        top_scores=top_scores.float().numpy(), top_indices=top_indices.numpy(),
+                        masks=masks.numpy(), weighted=weighted.numpy(),
+                        argmax=torch.argmax(scores).numpy(), maxval=torch.max(scores).float().numpy())
+
+
+if __name__ == "__main__":
+    assert refimport.available(), "/root/reference is required to mint fixtures"
+    torch.set_num_threads(1)
+    golden_poses()
+    golden_geometry()
+    golden_crop()
+    golden_dino_forward()
+    golden_score()
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)

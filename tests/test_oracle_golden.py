@@ -1,0 +1,132 @@
+"""CPU: the oracle restatements against fixtures minted from the reference's own code
+(tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import torch
+
+from oracle import crop as ocrop
+from oracle import score as oscore
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_generate_poses_matches_reference(golden):
+    from freepose_b200.pipeline.utils import generate_poses
+    g = golden["poses"]
+    assert np.array_equal(np.array(generate_poses(42)), g["p42"])
+    p600 = np.array(generate_poses(600))
+    assert np.array_equal(p600[:8], g["p600_first8"]) and np.array_equal(p600[-8:], g["p600_last8"])
+    assert sha(p600) == str(g["p600_sha"])
+    p20k = np.array(generate_poses(20000))
+    assert sha(p20k) == str(g["p20000_sha"])
+    assert np.array_equal(p20k[[0, 1, 7777, 19999]], g["p20000_rows"])
+    # structure: proper rotations at distance 1.1
+    R = p600[:, :3, :3]
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-12)
+    assert np.allclose(np.linalg.det(R), 1.0) and np.all(p600[:, 2, 3] == 1.1)
+
+
+def test_geometry_matches_reference(golden):
+    from freepose_b200.pipeline import utils as U
+    g = golden["geometry"]
+    for i in range(4):
+        c = {k[len(f"c{i}_"):]: g[k] for k in g.files if k.startswith(f"c{i}_")}
+        pc = U.depthmap_to_pointcloud(c["depth"], c["Kt"])
+        assert pc.shape[0] == int(c["n_points"]) and sha(pc) == str(c["pc_sha"])
+        s = float(c["est_scale"])
+        pcc = pc.copy(); m = pcc.mean(axis=0); pcc -= m; pcc /= 0.25; pcc *= s; pcc += m
+        assert np.array_equal(U.get_z_from_pointcloud(c["bbox"], pcc, c["Kq"], c["T0"]), c["tco_coarse"])
+        pcf = pc.copy(); pcf /= 0.25; pcf *= s
+        assert np.array_equal(U.get_z_from_pointcloud(c["bbox"], pcf, c["Kq"], c["T0"]), c["tco_fine"])
+        assert np.array_equal(U.mask_to_bbox(c["depth"] > 0), c["bbox_of_mask"])
+        # the O(1) extents formulation the engine uses gives the same TCO (to fp64 round-off of the mean)
+        ext = np.array([pc[:, 0].min(), pc[:, 0].max(), pc[:, 1].min(), pc[:, 1].max(), pc[:, 0].sum(),
+                        pc[:, 1].sum(), pc[:, 2].sum(), pc.shape[0]])
+        for recentre, want in ((True, c["tco_coarse"]), (False, c["tco_fine"])):
+            dx, dy = U.rescaled_extents(ext, s, recentre)
+            got = U.tco_from_extents(c["bbox"], dx, dy, c["Kq"], c["T0"])
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_crop_resize_pad_matches_reference(golden):
+    g = golden["crop"]
+    rng = np.random.default_rng(int(g["rng_seed"]))
+    i = 0
+    while f"c{i}_spec" in g.files:
+        H, W, T = [int(v) for v in g[f"c{i}_spec"]]
+        ext = float(g[f"c{i}_ext"])
+        ext = int(ext) if ext == 0 else ext
+        boxes = g[f"c{i}_boxes"]
+        imgs = rng.random((len(boxes), 3, H, W)).astype(np.float32)  # same stream as the generator
+        assert sha(imgs) == str(g[f"c{i}_seed_imgs_sha"])
+        out = ocrop.crop_resize_pad(imgs, boxes, T, bbox_extend=ext, orig_size=(H, W))
+        assert sha(out) == str(g[f"c{i}_out_sha"]), f"crop case {i}"
+        if f"c{i}_out" in g.files:
+            assert np.array_equal(out, g[f"c{i}_out"])
+        i += 1
+    assert i == 6
+
+
+def test_extend_boxes_product_matches_oracle():
+    from freepose_b200.pipeline.bbox_utils import extend_boxes
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        w, h = 640, 480
+        x1, y1 = int(rng.integers(0, 600)), int(rng.integers(0, 440))
+        x2, y2 = int(rng.integers(x1 + 1, 640)), int(rng.integers(y1 + 1, 480))
+        for ext in (0, 0.2, 0.1):
+            got = extend_boxes(torch.tensor([[x1, y1, x2, y2]]), ext, w, h)[0].tolist()
+            assert got == list(ocrop.extend_box([x1, y1, x2, y2], ext, w, h))
+
+
+def test_dino_forward_slices_match_reference(golden):
+    """oracle forward_features + token slices == the reference's DINOv2FeatureExtractor.forward output."""
+    from freepose_b200.vit_weights import synthetic_state_dict
+    from oracle.pipeline import reference_normalize
+    from oracle.vit import OracleViT
+    g = golden["dino_forward"]
+    vit = OracleViT(synthetic_state_dict(seed=3, depth=2)).float()
+    imgs = torch.from_numpy(g["imgs"])
+    with torch.no_grad():
+        for layer in (1, 2):
+            x = vit.forward_features(reference_normalize(imgs), layer)
+            np.testing.assert_allclose(x[:, 0].numpy(), g[f"cls_{layer}"], rtol=0, atol=2e-5)  # fp32 round-off (BLAS thread count)
+            np.testing.assert_allclose(x[:, 1:5].numpy(), g[f"reg_{layer}"], rtol=0, atol=2e-5)  # fp32 round-off (BLAS thread count)
+            np.testing.assert_allclose(x[:, 5:].numpy(), g[f"patch_{layer}"], rtol=0, atol=2e-5)  # fp32 round-off (BLAS thread count)
+
+
+def test_score_oracles_match_reference_lines(golden):
+    g = golden["score"]
+    ft = torch.from_numpy(g["feats_t"]).view(torch.bfloat16)
+    fq = torch.from_numpy(g["feat_q"]).view(torch.bfloat16)
+    ref_scores = g["scores"]
+    # the reference lines re-executed here reproduce the fixture bit for bit
+    assert np.array_equal(oscore.reference_scores(ft, fq).float().numpy(), ref_scores)
+    # the engine-order restatement: identical values on this fixture (at most 1 bf16 ulp apart in general)
+    eng = oscore.engine_order_scores(ft, fq)
+    assert np.array_equal(eng, ref_scores)
+    idx, vals = oscore.stable_topk(eng, 3)
+    assert np.array_equal(vals, g["top_scores"])             # values are tie-order independent
+    assert eng[3] == eng[5]                                    # the planted exact tie
+    assert int(idx[0]) == int(g["argmax"]) or eng[int(g["argmax"])] == vals[0]
+    assert float(g["maxval"]) == float(vals[0])
+    w = torch.from_numpy(g["masks"])
+    np.testing.assert_allclose(oscore.engine_order_scores(ft, fq, weights=w), g["weighted"], rtol=2e-6)
+    np.testing.assert_allclose(oscore.reference_scores(ft, fq, weights=w).numpy(), g["weighted"], rtol=1e-6)
+
+
+def test_ffa_oracles_agree():
+    torch.manual_seed(0)
+    feats = torch.randn(5, 16, 1024).to(torch.bfloat16)
+    rng = np.random.default_rng(0)
+    masks = rng.random((5, 56, 56)) > 0.995
+    masks[4] = False  # empty mask -> NaN row, which the reference detects and skips
+    ref = oscore.ffa_reference(feats, masks)
+    eng, counts = oscore.ffa_engine_order(feats, masks)
+    assert counts[4] == 0 and np.isnan(eng[4]).all() and np.isnan(ref[4]).all()
+    # sequential vs ATen summation order: identical up to rare single bf16-ulp flips
+    d = np.abs(ref[:4] - eng[:4])
+    assert (d > 0).mean() < 0.01 and np.all(d <= np.abs(ref[:4]) * 2 ** -7 + 1e-30)

@@ -1,0 +1,60 @@
+"""CPU: pins the ViT oracle.  The hub source of dinov2_vitl14_reg is not in /root/reference (third party,
+unpinned), so the oracle's architecture is pinned against the independent implementation installed here:
+transformers' Dinov2WithRegistersModel with the same weights."""
+import pytest
+import torch
+
+from freepose_b200.vit_weights import VITL14_REG, interpolated_pos_embed, synthetic_state_dict
+from oracle.vit import OracleViT, to_hf_state_dict
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synthetic_state_dict(seed=0, depth=3)
+
+
+@pytest.mark.parametrize("res", [224, 56, 518])
+def test_fp32_oracle_equals_transformers(sd, res):
+    from transformers import Dinov2WithRegistersConfig, Dinov2WithRegistersModel
+    cfg = Dinov2WithRegistersConfig(hidden_size=1024, num_hidden_layers=3, num_attention_heads=16, mlp_ratio=4,
+                                    patch_size=14, image_size=518, num_register_tokens=4)
+    hf = Dinov2WithRegistersModel(cfg).eval()
+    hf.load_state_dict({k: v.float() for k, v in to_hf_state_dict(sd).items()}, strict=True)
+    torch.manual_seed(res)
+    x = torch.randn(1, 3, res, res)
+    with torch.no_grad():
+        hs = hf(pixel_values=x, output_hidden_states=True)
+        mine = OracleViT(sd).float()
+        t = mine.prepare_tokens_with_masks(x)
+        assert torch.allclose(t, hs.hidden_states[0], atol=1e-5)
+        for i, blk in enumerate(mine.blocks):
+            t = blk(t)
+            assert torch.allclose(t, hs.hidden_states[i + 1], atol=2e-4), f"block {i}"
+        assert torch.allclose(mine.norm(t), hs.last_hidden_state, atol=2e-4)
+        assert t.shape[1] == VITL14_REG.num_tokens(res)
+
+
+def test_contract_mode_tracks_eager_bf16(sd):
+    """The explicit rounding contract and native PyTorch-eager bf16 are two realisations of the same arithmetic:
+    after a few blocks they agree to bf16 rounding noise, and both sit at the same distance from fp32."""
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 224, 224).to(torch.bfloat16)
+    with torch.no_grad():
+        eager = OracleViT(sd).to(torch.bfloat16).forward_features(x, 3).float()
+        contract = OracleViT(sd, contract=True).forward_features(x.float(), 3)
+        full = OracleViT(sd).float().forward_features(x.float(), 3)
+    assert rel_l2(eager, contract) < 5e-3
+    e_err, c_err = rel_l2(eager, full), rel_l2(contract, full)
+    assert c_err < 1.25 * e_err and e_err < 1.25 * c_err
+    # contract values are exactly representable in bf16
+    assert torch.equal(contract, contract.to(torch.bfloat16).float())
+
+
+def test_pos_embed_interpolation_identity_at_native_grid(sd):
+    p = interpolated_pos_embed(sd, VITL14_REG, 518)
+    assert torch.equal(p, sd["pos_embed"][0])
+    assert interpolated_pos_embed(sd, VITL14_REG, 224).shape == (257, 1024)
