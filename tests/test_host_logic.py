@@ -85,7 +85,7 @@ WORKER = textwrap.dedent("""
     dist.all_gather_object(gathered, idx.tolist())
     assert all(x == gathered[0] for x in gathered)               # every rank picks the identical winners
     dist.barrier()
-    print("rank", rank, "ok")
+    sys.stdout.write("rank" + str(rank) + "-ok" + chr(10)); sys.stdout.flush()
 """)
 
 
@@ -97,4 +97,4 @@ def test_score_allgather_two_ranks_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0-ok" in r.stdout and "rank1-ok" in r.stdout
