@@ -47,6 +47,12 @@ SIGNATURES = {
     "fp_abi_version": (_i, []),
     "fp_last_error": (C.c_char_p, []),
     "fp_device_sm_count": (_i, []),
+    "fp_launch_count": (C.c_longlong, []),
+    "fp_profile_enable": (None, [_i]),
+    "fp_profile_reset": (None, []),
+    "fp_profile_num_kinds": (_i, []),
+    "fp_profile_kind_name": (C.c_char_p, [_i]),
+    "fp_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "fp_vit_workspace_bytes": (_sz, [_i, _i]),
     "fp_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fp_gemm_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),

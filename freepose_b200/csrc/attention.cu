@@ -327,6 +327,7 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   }
   const int npairs = B * H;
   const int grid = npairs < sm_count() ? npairs : sm_count();
+  ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
   attention_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
   FP_CUDA(cudaGetLastError());
   return 0;

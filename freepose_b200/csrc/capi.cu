@@ -16,6 +16,14 @@ extern "C" {
 FP_API int fp_abi_version(void) { return FP_ABI_VERSION; }
 FP_API const char* fp_last_error(void) { return fp::last_error(); }
 FP_API int fp_device_sm_count(void) { return fp::sm_count(); }
+FP_API long long fp_launch_count(void) { return fp::launch_count(); }
+FP_API void fp_profile_enable(int on) { fp::prof_enable(on); }
+FP_API void fp_profile_reset(void) { fp::prof_reset(); }
+FP_API int fp_profile_num_kinds(void) { return fp::PROF_NUM_KINDS; }
+FP_API const char* fp_profile_kind_name(int kind) { return fp::prof_name(kind); }
+FP_API int fp_profile_collect(int kind, double* total_ms, double* total_work, long long* launches) {
+  return fp::prof_collect(kind, total_ms, total_work, launches);
+}
 
 FP_API size_t fp_vit_workspace_bytes(int batch, int res) { return fp::vit_workspace_bytes(batch, res); }
 

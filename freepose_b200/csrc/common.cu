@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace fp {
 
@@ -33,6 +35,65 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+// ---------------------------------------------------------------------------------------------- profiler
+namespace {
+struct ProfRec { cudaEvent_t a, b; int kind; double work; int launches; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_event_pool;
+std::atomic<long long> g_launches{0};
+const char* kProfNames[PROF_NUM_KINDS] = {"gemm_qkv", "gemm_proj", "gemm_fc1_gelu", "gemm_fc2", "gemm_patch_embed",
+                                          "attention", "layernorm", "token_prep", "score_topk", "raster", "geometry"};
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(int kind, double work, int launches, cudaStream_t s) : idx(-1), stream(s) {
+  g_launches += launches;
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{get_event(), get_event(), kind, work, launches};
+  cudaEventRecord(r.a, s);
+  g_recs.push_back(r);
+  idx = int(g_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_recs[idx].b, stream);
+}
+
+void prof_enable(int on) { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_on = on != 0; }
+void prof_reset() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_recs.clear();
+}
+const char* prof_name(int kind) { return (kind >= 0 && kind < PROF_NUM_KINDS) ? kProfNames[kind] : ""; }
+long long launch_count() { return g_launches.load(); }
+// Sums the event-timed durations of `kind` (synchronises on the recorded events).
+int prof_collect(int kind, double* total_ms, double* total_work, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0, work = 0;
+  long long n = 0;
+  for (auto& r : g_recs) {
+    if (r.kind != kind) continue;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(profile)");
+    float t = 0.f;
+    e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime(profile)");
+    ms += t; work += r.work; n += r.launches;
+  }
+  *total_ms = ms; *total_work = work; *launches = n;
+  return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -34,6 +34,22 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 
 // ------------------------------------------------------------------------------------------------
+// Launch accounting + optional CUDA-event timing per kernel family (bench.py's live roofline numbers).
+// ------------------------------------------------------------------------------------------------
+enum ProfKind {
+  PROF_GEMM_QKV = 0, PROF_GEMM_PROJ, PROF_GEMM_FC1, PROF_GEMM_FC2, PROF_GEMM_PATCH, PROF_ATTENTION, PROF_LAYERNORM,
+  PROF_TOKEN_PREP, PROF_SCORE, PROF_RASTER, PROF_GEOMETRY, PROF_NUM_KINDS
+};
+// RAII: counts `launches` kernel launches and, when profiling is enabled, brackets them with events on `stream`.
+// `work` is the algorithmic work of the bracketed launches (FLOPs for tensor kinds, bytes for HBM kinds).
+struct ProfScope {
+  ProfScope(int kind, double work, int launches, cudaStream_t stream);
+  ~ProfScope();
+  int idx;
+  cudaStream_t stream;
+};
+
+// ------------------------------------------------------------------------------------------------
 // bf16 helpers.  All "round" steps are round-to-nearest-even, the rounding ATen applies when an
 // op's output dtype is bf16.
 // ------------------------------------------------------------------------------------------------

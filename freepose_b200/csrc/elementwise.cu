@@ -133,6 +133,7 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int r
   if (rows <= 0) return 0;
   FP_REQUIRE(rows_per_group > 0, "layernorm: rows_per_group must be positive");
   const int blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  ProfScope prof(PROF_LAYERNORM, 2.0 * double(rows) * D * 2, 1, stream);
   layernorm_kernel<<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
                                                          rows_per_group);
   FP_CUDA(cudaGetLastError());
@@ -151,6 +152,7 @@ int im2col_patches(const void* img, int src_is_f32, bf16* out, int B, int res, i
   if (B <= 0) return 0;
   const int g = res / 14;
   const size_t total = size_t(B) * g * g * Kpad;
+  ProfScope prof(PROF_TOKEN_PREP, double(total) * 2 + double(B) * 3 * res * res * (src_is_f32 ? 4 : 2), 1, stream);
   if (src_is_f32)
     im2col_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(img, out, B, res, g, Kpad);
   else
@@ -162,6 +164,7 @@ int im2col_patches(const void* img, int src_is_f32, bf16* out, int B, int res, i
 int normalize_image(const float* img, bf16* out, int B, int res, cudaStream_t stream) {
   if (B <= 0) return 0;
   const size_t total = size_t(B) * 3 * res * res;
+  ProfScope prof(PROF_TOKEN_PREP, double(total) * 6, 1, stream);
   normalize_kernel<<<grid_for(total, 256), 256, 0, stream>>>(img, out, B, res);
   FP_CUDA(cudaGetLastError());
   return 0;
@@ -170,6 +173,7 @@ int normalize_image(const float* img, bf16* out, int B, int res, cudaStream_t st
 int write_special_tokens(const bf16* special, bf16* tokens, int B, int T, int n_special, int D, cudaStream_t stream) {
   FP_REQUIRE(D % 8 == 0, "special tokens: D must be a multiple of 8");
   if (B <= 0 || n_special <= 0) return 0;
+  ProfScope prof(PROF_TOKEN_PREP, double(B) * n_special * D * 2, 1, stream);
   special_tokens_kernel<<<B * n_special, 128, 0, stream>>>(special, tokens, B, T, n_special, D);
   FP_CUDA(cudaGetLastError());
   return 0;

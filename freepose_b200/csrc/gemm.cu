@@ -246,6 +246,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cuda
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int kind = MODE == EPI_PATCH_EMBED ? PROF_GEMM_PATCH
+                   : MODE == EPI_BIAS_GELU ? PROF_GEMM_FC1
+                   : MODE == EPI_BIAS      ? PROF_GEMM_QKV
+                   : (p.K > 1024 ? PROF_GEMM_FC2 : PROF_GEMM_PROJ);
+  ProfScope prof(kind, 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
   gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
   FP_CUDA(cudaGetLastError());
   return 0;

@@ -256,6 +256,7 @@ int mask_bbox(const float* depth, int B, int res, int fallback_lo, int fallback_
               int32_t* bbox_out, int32_t* count_out, uint8_t* mask_out, cudaStream_t stream) {
   FP_REQUIRE(res > 0 && res % 4 == 0, "mask_bbox: resolution must be a multiple of 4");
   if (B <= 0) return 0;
+  ProfScope prof(PROF_GEOMETRY, double(B) * res * res * 4, 1, stream);
   mask_bbox_kernel<<<B, 256, 0, stream>>>(depth, res, fallback_lo, fallback_hi, min_count, bbox_out, count_out,
                                           mask_out);
   FP_CUDA(cudaGetLastError());
@@ -274,6 +275,7 @@ int crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, co
   const int g = T / 14;
   const int total = dst_is_patches ? g * g * Kpad : 3 * T * T;
   const dim3 grid(min((total + 255) / 256, 64), B);
+  ProfScope prof(PROF_GEOMETRY, double(B) * total * (dst_is_patches ? 2 : 4), 1, stream);
   if (src_is_u8_hwc && dst_is_patches)
     crop_kernel<true, true><<<grid, 256, 0, stream>>>(src, boxes, 0, norm_lut, dst, src_h, src_w, T, Kpad, status);
   else if (src_is_u8_hwc)
@@ -287,6 +289,7 @@ int crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, co
 int depth_extents(const float* depth, const int32_t* view_idx, int n_out, int res, const double* kinv_dev,
                   double* out, cudaStream_t stream) {
   if (n_out <= 0) return 0;
+  ProfScope prof(PROF_GEOMETRY, double(n_out) * res * res * 4, 1, stream);
   depth_extents_kernel<<<n_out, 256, 0, stream>>>(depth, view_idx, res, kinv_dev, out);
   FP_CUDA(cudaGetLastError());
   return 0;

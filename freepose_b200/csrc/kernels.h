@@ -10,6 +10,11 @@ namespace fp {
 typedef __nv_bfloat16 bf16;
 
 const char* last_error();
+void prof_enable(int on);
+void prof_reset();
+const char* prof_name(int kind);
+long long launch_count();
+int prof_collect(int kind, double* total_ms, double* total_work, long long* launches);
 
 // ---------------------------------------------------------------------------------------- GEMM
 enum EpilogueMode { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_LS_RES = 2, EPI_PATCH_EMBED = 3 };

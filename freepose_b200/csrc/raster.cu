@@ -318,6 +318,7 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(
       reinterpret_cast<uint8_t*>(workspace) + align_up(size_t(a.B) * a.V * sizeof(ScreenVertex), 256));
   const size_t nkeys = size_t(a.B) * a.res * a.res * a.msaa;
+  ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, 4, stream);  // algorithmic bytes: RGB u8 + depth f32 out
   clear_keys_kernel<<<sm_count() * 8, 256, 0, stream>>>(keys, nkeys);
   FP_CUDA(cudaGetLastError());
   vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy);

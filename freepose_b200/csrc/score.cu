@@ -246,6 +246,7 @@ int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, in
   FP_REQUIRE(workspace_bytes >= score_workspace_bytes(B, P, D), "score: workspace too small");
   FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "score: workspace must be 16-byte aligned");
   if (B == 0) return 0;
+  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, k > 0 ? 3 : 2, stream);
   bf16* qn = reinterpret_cast<bf16*>(workspace);
   uint8_t* taken = reinterpret_cast<uint8_t*>(workspace) + size_t(P) * D * sizeof(bf16);
   prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query);
@@ -266,6 +267,7 @@ int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val,
   FP_REQUIRE(k >= 0 && k <= B, "topk: k=%d out of range for B=%d", k, B);
   FP_REQUIRE(workspace_bytes >= size_t(B), "topk: workspace too small");
   if (k == 0) return 0;
+  ProfScope prof(PROF_SCORE, double(B) * 4, 1, stream);
   topk_kernel<<<1, 1024, 0, stream>>>(scores, B, k, topk_idx, topk_val, reinterpret_cast<uint8_t*>(workspace));
   FP_CUDA(cudaGetLastError());
   return 0;
@@ -276,6 +278,7 @@ int ffa_pool(const bf16* feats, const uint8_t* masks, int V, int res, int g, int
   FP_REQUIRE(res == g * 14, "ffa: mask resolution %d != 14 * grid %d", res, g);
   FP_REQUIRE(D % 2 == 0, "ffa: D must be even");
   if (V <= 0) return 0;
+  ProfScope prof(PROF_SCORE, double(V) * g * g * D * 2, 1, stream);
   ffa_kernel<<<V, 256, size_t(g) * g, stream>>>(feats, masks, res, g, D, out, valid);
   FP_CUDA(cudaGetLastError());
   return 0;

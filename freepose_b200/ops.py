@@ -75,7 +75,7 @@ def normalize_image(image: torch.Tensor):
 
 # ------------------------------------------------------------------------------------------- score
 def score_topk(feats_t: torch.Tensor, feat_q: torch.Tensor, k: int = 3, weights=None, normalise_query=True,
-               return_patch_scores=False):
+               return_patch_scores=False, scores_out: torch.Tensor | None = None):
     """Position-aligned per-patch cosine + mean + top-k (fp_score_topk).
 
     feats_t (B,P,D) bf16, feat_q (P,D) or (1,P,D) bf16.  Returns (scores fp32 (B,), idx int32 (k,),
@@ -87,7 +87,11 @@ def score_topk(feats_t: torch.Tensor, feat_q: torch.Tensor, k: int = 3, weights=
     dev = feats_t.device
     lib = load()
     ws = _ws(lib.fp_score_workspace_bytes(B, P, D), dev)
-    scores = torch.empty(B, dtype=torch.float32, device=dev)
+    if scores_out is not None:  # e.g. this rank's slice of the all-gather buffer: no copy between score and NCCL
+        assert scores_out.dtype == torch.float32 and scores_out.numel() >= B and scores_out.is_contiguous()
+        scores = scores_out[:B]
+    else:
+        scores = torch.empty(B, dtype=torch.float32, device=dev)
     idx = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
     vals = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
     patch = torch.empty(B, P, dtype=torch.float32, device=dev) if return_patch_scores else None
@@ -213,7 +217,7 @@ def depth_extents(depth: torch.Tensor, K, view_idx=None):
     """(n,8) fp64: xmin,xmax,ymin,ymax,sum_x,sum_y,sum_z,count of K^-1 [u v 1]^T d over non-zero points."""
     B, res, _ = depth.shape
     dev = depth.device
-    kinv = torch.from_numpy(np.linalg.inv(np.asarray(K))).to(torch.float64).reshape(9).to(dev)
+    kinv = torch.from_numpy(np.linalg.inv(np.asarray(K, dtype=np.float64))).to(torch.float64).reshape(9).to(dev)
     if view_idx is not None:
         view_idx = view_idx.to(torch.int32).contiguous()
         n = view_idx.numel()

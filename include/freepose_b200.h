@@ -36,6 +36,17 @@ FP_API int fp_abi_version(void);
 FP_API const char* fp_last_error(void);
 FP_API int fp_device_sm_count(void);
 
+/* Launch accounting and per-kernel-family CUDA-event timing (used by bench.py for gpu_launches and the live
+ * roofline numbers; no reference counterpart -- the reference has no timers). */
+FP_API long long fp_launch_count(void);            /* kernels launched by this library so far               */
+FP_API void fp_profile_enable(int on);             /* bracket every launch with events on its stream        */
+FP_API void fp_profile_reset(void);
+FP_API int fp_profile_num_kinds(void);
+FP_API const char* fp_profile_kind_name(int kind);
+/* host out: summed event time (ms), summed algorithmic work (FLOPs for the gemm and attention kinds, bytes otherwise),
+ * launches.  Synchronises on the recorded events. */
+FP_API int fp_profile_collect(int kind, double* total_ms, double* total_work, long long* launches);
+
 /* ------------------------------------------------------------------------------------------------
  * DINOv2 ViT-L/14-reg feature extractor
  * replaces: src/pipeline/retrieval/dino.py:14-32  (DINOv2FeatureExtractor.forward:
