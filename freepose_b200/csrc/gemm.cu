@@ -28,7 +28,8 @@ constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_GROUPS = 3;                   // warps per TMEM lane quarter (column chunks are dealt round-robin)
+constexpr int NUM_EPI_WARPS = 4 * NUM_EPI_GROUPS;   // 12: three per SM sub-partition hide the epilogue's ALU/MUFU latency
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -45,21 +46,80 @@ struct Params {
   int token_offset;
 };
 
-// erf with |abs err| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): far below half a bf16 ulp of the GELU output,
-// at ~12 issue slots instead of libdevice erff's ~25 (the fc1 epilogue must fit under the MMA time).
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p, e, 1.0f), x);
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per issue slot) -------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16x2 bits -> the two values as an fp32 pair
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t v) { return pack2(bf16lo(v), bf16hi(v)); }
+// round an fp32 pair to bf16 (RN-even) and return it again as fp32 pair (values now bf16-representable)
+__device__ __forceinline__ f32x2 round2_bf16(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return bf16x2_to_f32x2(pack_bf16x2(lo, hi));
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
 }
 
-__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erf_fast(u * 0.70710678118654752f)); }
+// GELU(erf) of two values.  erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below half a bf16 ulp of
+// the result) with approximate MUFU rcp / ex2, written so that no select is needed:
+//   gelu(u) = u/2 + |u|/2 * erf(|u|/sqrt2),   erf(a) = 1 - (a1 t + ... + a5 t^5) exp(-a^2),  t = 1/(1 + p a)
+// ~11.5 issue slots per element instead of ~39 for libdevice erff (the fc1 epilogue has to fit under the MMA time).
+__device__ __forceinline__ f32x2 gelu2(f32x2 u) {
+  const f32x2 z = mul2(u, splat2(0.70710678118654752f));
+  float z0, z1;
+  unpack2(z, z0, z1);
+  const f32x2 az = pack2(fabsf(z0), fabsf(z1));
+  float d0, d1;
+  unpack2(fma2(az, splat2(0.3275911f), splat2(1.0f)), d0, d1);
+  const f32x2 t = pack2(rcp_fast(d0), rcp_fast(d1));
+  f32x2 pl = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  pl = fma2(pl, t, splat2(1.421413741f));
+  pl = fma2(pl, t, splat2(-0.284496736f));
+  pl = fma2(pl, t, splat2(0.254829592f));
+  pl = mul2(pl, t);
+  float e0, e1;
+  unpack2(mul2(mul2(z, z), splat2(-1.4426950408889634f)), e0, e1);
+  const f32x2 e = pack2(ex2_fast(e0), ex2_fast(e1));
+  const f32x2 erf_abs = fma2(mul2(pl, splat2(-1.0f)), e, splat2(1.0f));  // erf(|z|)
+  const f32x2 half_abs_u = mul2(az, splat2(0.70710678118654752f));       // |u| / 2
+  return fma2(half_abs_u, erf_abs, mul2(u, splat2(0.5f)));
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -150,8 +210,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // column half of the tile
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;   // 0..NUM_EPI_GROUPS-1: which column chunks of the tile this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -169,8 +229,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int col0 = half * 128 + chunk * 32;
+      for (int chunk = grp; chunk < BN / 32; chunk += NUM_EPI_GROUPS) {
+        const int col0 = chunk * 32;
         const int gcol = n_blk * BN + col0;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
@@ -207,19 +267,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t ow[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float v0 = __uint_as_float(r[i * 8 + j * 2]) + bf16lo(bw[j]);
-              float v1 = __uint_as_float(r[i * 8 + j * 2 + 1]) + bf16hi(bw[j]);
+              // two adjacent columns at a time in packed fp32x2
+              f32x2 v = add2(pack2(__uint_as_float(r[i * 8 + j * 2]), __uint_as_float(r[i * 8 + j * 2 + 1])),
+                             bf16x2_to_f32x2(bw[j]));
               if (MODE == EPI_BIAS_GELU) {
-                v0 = gelu_erf(bf16_round(v0));
-                v1 = gelu_erf(bf16_round(v1));
+                v = gelu2(round2_bf16(v));
               } else if (MODE == EPI_BIAS_LS_RES) {
-                v0 = bf16lo(xw[j]) + bf16_round(bf16_round(v0) * bf16lo(gw[j]));
-                v1 = bf16hi(xw[j]) + bf16_round(bf16_round(v1) * bf16hi(gw[j]));
+                v = round2_bf16(mul2(round2_bf16(v), bf16x2_to_f32x2(gw[j])));
+                v = add2(v, bf16x2_to_f32x2(xw[j]));
               } else if (MODE == EPI_PATCH_EMBED) {
-                v0 = bf16_round(v0) + bf16lo(xw[j]);
-                v1 = bf16_round(v1) + bf16hi(xw[j]);
+                v = add2(round2_bf16(v), bf16x2_to_f32x2(xw[j]));
               }
-              ow[j] = pack_bf16x2(v0, v1);
+              ow[j] = f32x2_to_bf16x2(v);
             }
             optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }

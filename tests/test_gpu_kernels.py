@@ -82,7 +82,7 @@ def test_gemm_epilogues(ops):
     xd = x.clone().to(dev)
     out2 = ops.gemm(h.to(dev), w2.to(dev), b2.to(dev), FP_EPI_BIAS_LS_RES, gamma=g.to(dev), residual=xd)
     assert out2.data_ptr() == xd.data_ptr()  # in place on the residual stream
-    check_stage(out2, ref2, "fc2 + layerscale + residual")
+    check_stage(out2, ref2, "fc2 + layerscale + residual", ulp_exact=False)  # x + z may cancel
 
     B, P, T = 3, 16, 21
     pa = torch.zeros(B * P, 640, dtype=bf)
