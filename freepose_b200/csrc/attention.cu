@@ -1,17 +1,23 @@
-// ViT self-attention on tcgen05: one persistent CTA per SM walks over
-// (image, head) pairs; the whole key set of one head (T <= 272 tokens: 261 at 224^2) lives in shared
-// memory, so softmax is single-pass (no online rescale):
+// ViT self-attention on tcgen05.  One persistent CTA per SM walks over
+// (image, head) pairs; all keys of one head (T <= 272 tokens: 261 at 224^2) sit in shared memory, so softmax is
+// single pass (no online rescale).
 //
-//   warp 0      TMA loader   K,V (double buffered across pairs) and the pair's Q tiles (128 rows each)
-//   warp 1      MMA issuer   S = Q K^T  (M128 x N{256,+16} x K64, fp32 in TMEM)
-//                            O = P V    (M128 x N64, P from a swizzled smem ring, V as MN-major operand)
-//   warp 2      TMEM allocator
-//   warps 4..7  softmax      thread = query row: row max, p = exp2((s - max) * scale*log2e) in fp32,
-//                            row sum of the unrounded p, P rounded to bf16 into the smem ring in 64-key
-//                            chunks (so P.V overlaps the exponentials), finally O / rowsum -> bf16 -> HBM.
+//   warp 0       TMA loader   K,V (double buffered across pairs), Q tiles through a 2-slot ring
+//   warp 1       MMA issuer   S = Q K^T (M128 x N{256,+16} x K64, fp32 accumulators in TMEM)
+//                             O = P V   (P read straight from TMEM -- "TS" form --, V as MN-major smem operand)
+//   warp 2       TMEM allocator
+//   warps 4..11  softmax      two warps per TMEM lane quarter split the key columns of every row: row max,
+//                             p = exp2((s - max) * scale*log2e) in fp32, row sum of the unrounded p, P rounded to
+//                             bf16 and stored back into TMEM with tcgen05.st (no shared-memory round trip), then
+//                             O / rowsum -> bf16 -> HBM.
 //
-// Arithmetic contract = flash/xformers attention (oracle/vit.py contract_attention): logits and softmax
-// statistics in fp32, un-normalised P rounded to bf16 for the tensor-core P.V, one rounding of O.
+// Token counts such as 261 = 2*128 + 5 leave a query tile with only a handful of rows (cls + registers).  With one
+// row per thread that tile would cost as many exponential issue slots as a full one, so remainders of <= 16 rows take
+// a TRANSPOSED path: S^T = K Q_r^T (keys along TMEM lanes, the few queries along columns), softmax statistics by
+// warp shuffles across keys, P^T transposed through a small smem staging buffer into the TMEM P operand.
+//
+// Arithmetic contract = flash/xformers attention (oracle/vit.py contract_attention): logits and softmax statistics
+// in fp32, un-normalised P rounded to bf16 for the tensor-core P.V, one rounding of O.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,35 +25,39 @@ namespace fp {
 
 namespace {
 
-constexpr int HD = 64;            // head dim
-constexpr int QT = 128;           // query rows per tile
-constexpr int MAX_TPAD = 272;     // padded key count (multiple of 16)
-constexpr int MAX_QTILES = 3;
+constexpr int HD = 64;             // head dim
+constexpr int QT = 128;            // query rows per tile
+constexpr int MAX_TPAD = 272;      // padded key count (multiple of 16)
 constexpr int ROW_BYTES = HD * 2;  // 128 B: one swizzle row
-constexpr int Q_TILE_BYTES = QT * ROW_BYTES;       // 16 KB
-constexpr int KV_BYTES = MAX_TPAD * ROW_BYTES;     // 34 KB
-constexpr int P_CHUNK_KEYS = 64;
-constexpr int P_CHUNK_BYTES = QT * 128;            // 16 KB
-constexpr int P_STAGES = 2;
-constexpr int NUM_THREADS = 256;
+constexpr int Q_TILE_BYTES = QT * ROW_BYTES;    // 16 KB
+constexpr int KV_BYTES = MAX_TPAD * ROW_BYTES;  // 34 KB
+constexpr int SPECIAL_MAX = 16;    // remainder rows handled by the transposed path
+constexpr int NUM_SOFTMAX_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_SOFTMAX_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0;
-constexpr int O_COL = 384;
+constexpr int S_COL = 0;      // 272 fp32 columns (transposed path: 3 x 16 columns)
+constexpr int P_COL = 272;    // 136 columns of packed bf16x2
+constexpr int O_COL = 408;    // 64 fp32 columns
+constexpr int MAX_CHUNKS = 5; // 64-key chunks of P
+constexpr int P3_STRIDE = 288;  // bf16 elements per staged P^T row (272 keys + pad)
 
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + MAX_QTILES * Q_TILE_BYTES;  // 2 buffers
-constexpr int OFF_V = OFF_K + 2 * KV_BYTES;               // 2 buffers
-constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
-constexpr int OFF_BAR = OFF_P + P_STAGES * P_CHUNK_BYTES;
+constexpr int OFF_Q = 0;                           // 2 ring slots
+constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;    // 2 buffers
+constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
+constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2][128] max + [2][128] sum
+constexpr int OFF_RED = OFF_XCH + 4 * 128 * 4;     // float [8 warps][16] max + [8][16] sum
+constexpr int OFF_P3 = OFF_RED + 2 * 8 * 16 * 4;   // bf16 [16][P3_STRIDE]
+constexpr int OFF_BAR = OFF_P3 + SPECIAL_MAX * P3_STRIDE * 2;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 struct Params {
   bf16* out;
   int B, T, H;
-  int tpad;      // keys padded to a multiple of 16
-  int nq;        // query tiles per (image, head)
-  int nchunks;   // 64-key P chunks
-  float sl2;     // scale * log2(e)
+  int tpad;       // keys padded to a multiple of 16
+  int n_normal;   // query tiles handled row-per-thread
+  int n_special;  // remainder query rows (<= 16) handled by the transposed path, 0 if none
+  int nchunks;    // 64-key chunks
+  float sl2;      // scale * log2(e)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -55,38 +65,107 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// exponentials of 32 logits -> 16 packed bf16x2 words; returns the fp32 sum of the unrounded values.
+// MASKED: columns >= valid are forced to 0 (only the group that straddles T takes this path).
+template <bool MASKED>
+__device__ __forceinline__ float exp_group(const uint32_t (&v)[32], float sl2, float msl, int valid,
+                                           uint32_t (&packed)[16]) {
+  float part[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains instead of one 32-long dependency
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float e0 = ex2(fmaf(__uint_as_float(v[j]), sl2, -msl));
+    float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -msl));
+    if (MASKED) {
+      e0 = j < valid ? e0 : 0.f;
+      e1 = j + 1 < valid ? e1 : 0.f;
+    }
+    part[(j >> 1) & 3] += e0 + e1;
+    packed[j >> 1] = pack_bf16x2(e0, e1);
+  }
+  return (part[0] + part[1]) + (part[2] + part[3]);
+}
+
+template <bool MASKED>
+__device__ __forceinline__ float max_group(const uint32_t (&v)[32], int valid, float m) {
+  float part[4] = {m, m, m, m};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = (!MASKED || j < valid) ? __uint_as_float(v[j]) : -INFINITY;
+    part[j & 3] = fmaxf(part[j & 3], x);
+  }
+  return fmaxf(fmaxf(part[0], part[1]), fmaxf(part[2], part[3]));
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const Params p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQs,
+                 const __grid_constant__ CUtensorMap tmKV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
-  uint64_t* q_full = bars + 4;
-  uint64_t* q_empty = bars + 5;
-  uint64_t* s_full = bars + 6;
-  uint64_t* s_empty = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint64_t* o_empty = bars + 9;
-  uint64_t* p_full = bars + 10;    // [P_STAGES]
-  uint64_t* p_empty = bars + 12;   // [P_STAGES]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 4;     // [2]
+  uint64_t* q_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* s_empty = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint64_t* o_empty = bars + 11;
+  uint64_t* p_full = bars + 12;    // [MAX_CHUNKS]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12 + MAX_CHUNKS);
+  float* xch_max = reinterpret_cast<float*>(smem + OFF_XCH);        // [2][128]
+  float* xch_sum = xch_max + 2 * 128;                                // [2][128]
+  float* red_max = reinterpret_cast<float*>(smem + OFF_RED);        // [8][16]
+  float* red_sum = red_max + 8 * 16;                                 // [8][16]
+  bf16* p3s = reinterpret_cast<bf16*>(smem + OFF_P3);               // [16][P3_STRIDE]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = p.B * p.H;
   const int half_rows = p.tpad / 2;
+  const int tiles_per_pair = p.n_normal + (p.n_special > 0 ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmQs);
     tma_prefetch_desc(&tmKV);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    mbar_init(s_full, 1); mbar_init(s_empty, 4);
-    mbar_init(o_full, 1); mbar_init(o_empty, 4);
-    for (int i = 0; i < P_STAGES; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(s_full, 1); mbar_init(s_empty, NUM_SOFTMAX_WARPS);
+    mbar_init(o_full, 1); mbar_init(o_empty, NUM_SOFTMAX_WARPS);
+    for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&p_full[i], NUM_SOFTMAX_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -99,6 +178,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---------------------------------------------------------------------------- TMA loader
     if (lane == 0) {
       int it = 0;
+      uint32_t qi = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
         const int b = pair / p.H, h = pair - b * p.H;
         const int row0 = b * p.T;
@@ -112,10 +192,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_2d(sK + half_rows * ROW_BYTES, &tmKV, &kv_full[buf], kcol, row0 + half_rows);
         tma_load_2d(sV, &tmKV, &kv_full[buf], vcol, row0);
         tma_load_2d(sV + half_rows * ROW_BYTES, &tmKV, &kv_full[buf], vcol, row0 + half_rows);
-        mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, p.nq * Q_TILE_BYTES);
-        for (int t = 0; t < p.nq; ++t)
-          tma_load_2d(smem + OFF_Q + t * Q_TILE_BYTES, &tmQ, q_full, h * HD, row0 + t * QT);
+        for (int t = 0; t < tiles_per_pair; ++t, ++qi) {
+          const int slot = qi & 1;
+          mbar_wait(&q_empty[slot], ((qi >> 1) & 1) ^ 1);
+          uint8_t* sQ = smem + OFF_Q + slot * Q_TILE_BYTES;
+          if (t < p.n_normal) {
+            mbar_arrive_expect_tx(&q_full[slot], Q_TILE_BYTES);
+            tma_load_2d(sQ, &tmQ, &q_full[slot], h * HD, row0 + t * QT);
+          } else {
+            mbar_arrive_expect_tx(&q_full[slot], SPECIAL_MAX * ROW_BYTES);
+            tma_load_2d(sQ, &tmQs, &q_full[slot], h * HD, row0 + p.n_normal * QT);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -125,47 +213,61 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int n2 = p.tpad - n1;
       const uint32_t idesc_s1 = umma_idesc_bf16(QT, n1, 0, 0);
       const uint32_t idesc_s2 = umma_idesc_bf16(QT, n2 > 0 ? n2 : 16, 0, 0);
-      const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);  // B (= V) is MN-major
-      uint32_t s_iter = 0, p_iter = 0;
+      const uint32_t idesc_st = umma_idesc_bf16(QT, SPECIAL_MAX, 0, 0);  // S^T = K (M=keys) x Q_r^T (N=16)
+      const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);           // B (= V) is MN-major
+      uint32_t tile_iter = 0;
       int it = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t sK = smem_u32(smem + OFF_K + buf * KV_BYTES);
         const uint32_t sV = smem_u32(smem + OFF_V + buf * KV_BYTES);
         mbar_wait(&kv_full[buf], (it >> 1) & 1);
-        mbar_wait(q_full, it & 1);
-        tc_fence_after();
-        for (int t = 0; t < p.nq; ++t, ++s_iter) {
-          // ---- S = Q_t K^T
-          mbar_wait(s_empty, (s_iter & 1) ^ 1);
+        for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
+          const int slot = tile_iter & 1;
+          const uint32_t sQ = smem_u32(smem + OFF_Q + slot * Q_TILE_BYTES);
+          const bool special = t >= p.n_normal;
+          mbar_wait(&q_full[slot], (tile_iter >> 1) & 1);
+          mbar_wait(s_empty, (tile_iter & 1) ^ 1);
           tc_fence_after();
-          const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(smem + OFF_Q + t * Q_TILE_BYTES), 16, 1024);
-          const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
-          const uint64_t k_desc2 = umma_smem_desc_sw128(sK + 256 * ROW_BYTES, 16, 1024);
+          if (!special) {
+            // ---- S = Q_t K^T
+            const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
+            const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
+            const uint64_t k_desc2 = umma_smem_desc_sw128(sK + 256 * ROW_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            umma_bf16_ss(tmem_base + S_COL, q_desc + uint64_t(2 * k), k_desc1 + uint64_t(2 * k), idesc_s1, k != 0);
-            if (n2 > 0)
-              umma_bf16_ss(tmem_base + S_COL + 256, q_desc + uint64_t(2 * k), k_desc2 + uint64_t(2 * k), idesc_s2,
-                           k != 0);
+            for (int k = 0; k < HD / 16; ++k) {
+              umma_bf16_ss(tmem_base + S_COL, q_desc + uint64_t(2 * k), k_desc1 + uint64_t(2 * k), idesc_s1, k != 0);
+              if (n2 > 0)
+                umma_bf16_ss(tmem_base + S_COL + 256, q_desc + uint64_t(2 * k), k_desc2 + uint64_t(2 * k), idesc_s2,
+                             k != 0);
+            }
+          } else {
+            // ---- S^T = K Q_r^T : three 128-key row blocks, 16 query columns each
+            const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
+            for (int i = 0; i * QT < p.tpad; ++i) {
+              const uint64_t k_desc = umma_smem_desc_sw128(sK + uint32_t(i * QT) * ROW_BYTES, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k)
+                umma_bf16_ss(tmem_base + S_COL + 16 * i, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), idesc_st,
+                             k != 0);
+            }
           }
           umma_commit(s_full);
-          if (t == p.nq - 1) umma_commit(q_empty);
-          // ---- O = P V, chunk by chunk as the softmax warps produce P
-          mbar_wait(o_empty, (s_iter & 1) ^ 1);
+          umma_commit(&q_empty[slot]);
+          // ---- O = P V, P read from TMEM as the softmax warps store it
+          mbar_wait(o_empty, (tile_iter & 1) ^ 1);
           tc_fence_after();
-          for (int c = 0; c < p.nchunks; ++c, ++p_iter) {
-            const int slot = p_iter % P_STAGES;
-            mbar_wait(&p_full[slot], (p_iter / P_STAGES) & 1);
-            tc_fence_after();
-            const int keys = (p.tpad - c * P_CHUNK_KEYS) < P_CHUNK_KEYS ? (p.tpad - c * P_CHUNK_KEYS) : P_CHUNK_KEYS;
-            const uint64_t p_desc = umma_smem_desc_sw128(smem_u32(smem + OFF_P + slot * P_CHUNK_BYTES), 16, 1024);
-            for (int k = 0; k < keys / 16; ++k) {
-              const uint64_t v_desc =
-                  umma_smem_desc_sw128(sV + uint32_t(c * P_CHUNK_KEYS + k * 16) * ROW_BYTES, 1024, 1024);
-              umma_bf16_ss(tmem_base + O_COL, p_desc + uint64_t(2 * k), v_desc, idesc_pv, (c | k) != 0);
+          for (int c = 0; c < p.nchunks; ++c) {
+            if (!special || c == 0) {
+              mbar_wait(&p_full[c], tile_iter & 1);
+              tc_fence_after();
             }
-            umma_commit(&p_empty[slot]);
+            const int keys = (p.tpad - c * 64) < 64 ? (p.tpad - c * 64) : 64;
+            for (int k = 0; k < keys / 16; ++k) {
+              const int key0 = c * 64 + k * 16;
+              const uint64_t v_desc = umma_smem_desc_sw128(sV + uint32_t(key0) * ROW_BYTES, 1024, 1024);
+              umma_bf16_ts(tmem_base + O_COL, tmem_base + P_COL + uint32_t(key0 >> 1), v_desc, idesc_pv, key0 != 0);
+            }
           }
           umma_commit(o_full);
         }
@@ -174,122 +276,233 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------------------- softmax + epilogue
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // row inside the query tile
+    const int q = warp & 3;              // TMEM lane quarter
+    const int hf = (warp - 4) >> 2;      // which half of the key columns of a row this warp handles
+    const int sw = warp - 4;             // 0..7
+    const int r = q * 32 + lane;         // row inside the tile (= key inside a 128-key block on the transposed path)
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    uint32_t s_iter = 0, p_iter = 0;
+    const int ngroups = (p.tpad + 31) / 32;  // 32-column groups of S (the last one may hold 16 columns)
+    uint32_t tile_iter = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int b = pair / p.H, h = pair - b * p.H;
-      for (int t = 0; t < p.nq; ++t, ++s_iter) {
-        const bool warp_active = t * QT + q * 32 < p.T;  // any valid query row in this warp
-        const int tok = t * QT + r;
-        mbar_wait(s_full, s_iter & 1);
+      for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
+        const bool special = t >= p.n_normal;
+        const uint32_t par = tile_iter & 1;
+        mbar_wait(s_full, par);
         tc_fence_after();
-        // ---- pass 1: row max over the valid keys
-        float m = -INFINITY;
-        if (warp_active) {
-          for (int c0 = 0; c0 < p.tpad; c0 += 32) {
-            if (c0 + 32 <= p.tpad) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
-            } else {
-              uint32_t v[16];
-              tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
-            }
-          }
-        }
-        const float msl = m * p.sl2;
-        // ---- pass 2: exponentials, row sum, bf16 P chunks into the smem ring
-        float l = 0.f;
-        for (int c = 0; c < p.nchunks; ++c, ++p_iter) {
-          const int slot = p_iter % P_STAGES;
-          mbar_wait(&p_empty[slot], ((p_iter / P_STAGES) & 1) ^ 1);
+        if (!special) {
+          const bool warp_active = t * QT + q * 32 < p.T;  // any valid query row in this warp's lanes
+          const int tok = t * QT + r;
+          // ---- pass 1: row max (this warp: groups with g % 2 == hf)
+          float m = -INFINITY;
           if (warp_active) {
-            const int c0 = c * P_CHUNK_KEYS;
-            const int keys = (p.tpad - c0) < P_CHUNK_KEYS ? (p.tpad - c0) : P_CHUNK_KEYS;
-            uint8_t* prow = smem + OFF_P + slot * P_CHUNK_BYTES + r * 128;
-            for (int g0 = 0; g0 < keys; g0 += 32) {
+            for (int g = hf; g < ngroups; g += 2) {
+              const int c0 = g * 32;
+              const int width = p.tpad - c0 >= 32 ? 32 : 16;
               uint32_t v[32];
-              if (keys - g0 >= 32) {
-                tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0 + g0, v);
+              if (width == 32) {
+                tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
               } else {
-                uint32_t w[16];
-                tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0 + g0, w);
+                uint32_t w16[16];
+                tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[16 + j] = 0xff800000u; }
+                for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
               }
               tmem_ld_wait();
-              float e[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = ex2(fmaf(__uint_as_float(v[j]), p.sl2, -msl));
-                e[j] = (c0 + g0 + j < p.T) ? x : 0.f;
-                l += e[j];
-              }
-              const int nvec = (keys - g0 >= 32) ? 4 : 2;
-#pragma unroll
-              for (int jv = 0; jv < 4; ++jv)
-                if (jv < nvec) {
-                  const int chunk16 = (g0 >> 3) + jv;  // 16-byte chunk index inside the 128-byte row
-                  uint4 o;
-                  o.x = pack_bf16x2(e[jv * 8 + 0], e[jv * 8 + 1]);
-                  o.y = pack_bf16x2(e[jv * 8 + 2], e[jv * 8 + 3]);
-                  o.z = pack_bf16x2(e[jv * 8 + 4], e[jv * 8 + 5]);
-                  o.w = pack_bf16x2(e[jv * 8 + 6], e[jv * 8 + 7]);
-                  *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = o;
-                }
+              if (c0 + 32 <= p.T) m = max_group<false>(v, 32, m);
+              else                m = max_group<true>(v, p.T - c0, m);
             }
-            fence_proxy_async_smem();
           }
-          if (c == p.nchunks - 1) {
-            // all reads of S are complete -> the next tile's Q K^T may overwrite it
+          xch_max[hf * 128 + r] = m;
+          named_bar_sync(1 + q, 64);
+          m = fmaxf(xch_max[r], xch_max[128 + r]);
+          const float msl = m * p.sl2;
+          // ---- pass 2: exponentials, row sum, bf16 P into TMEM (chunk c: this warp owns keys [64c + 32hf, +32))
+          float l = 0.f;
+          for (int c = 0; c < p.nchunks; ++c) {
+            const int c0 = c * 64 + hf * 32;
+            if (warp_active && c0 < p.tpad) {
+              const int width = p.tpad - c0 >= 32 ? 32 : 16;
+              uint32_t v[32], pk[16];
+              if (width == 32) {
+                tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
+              } else {
+                uint32_t w16[16];
+                tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
+              }
+              tmem_ld_wait();
+              if (c0 + 32 <= p.T) l += exp_group<false>(v, p.sl2, msl, 32, pk);
+              else                l += exp_group<true>(v, p.sl2, msl, p.T - c0, pk);
+              if (width == 32) {
+                tmem_st_32x32b_x16(tmem_base + lane_addr + P_COL + (c0 >> 1), pk);
+              } else {
+                uint32_t pk8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
+                tmem_st_32x32b_x8(tmem_base + lane_addr + P_COL + (c0 >> 1), pk8);
+              }
+              tmem_st_wait();
+            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
+            if (c == p.nchunks - 1 && lane == 0) mbar_arrive(s_empty);  // all S reads of this warp are done
+            if (lane == 0) mbar_arrive(&p_full[c]);
           }
+          xch_sum[hf * 128 + r] = l;
+          named_bar_sync(1 + q, 64);
+          l = xch_sum[r] + xch_sum[128 + r];
+          // ---- epilogue: this warp normalises 32 of the 64 output columns
+          mbar_wait(o_full, par);
+          tc_fence_after();
+          uint32_t o[32];
+          if (warp_active) {
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, o);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[slot]);
-        }
-        // ---- epilogue: O / rowsum -> bf16 -> HBM
-        mbar_wait(o_full, s_iter & 1);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        if (warp_active) {
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL, o0);
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + 32, o1);
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-        if (warp_active && tok < p.T) {
-          const float inv = 1.0f / l;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * p.T + tok) * (p.H * HD) + h * HD);
+          if (lane == 0) mbar_arrive(o_empty);
+          if (warp_active && tok < p.T) {
+            const float inv = 1.0f / l;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * p.T + tok) * (p.H * HD) + h * HD + hf * 32);
 #pragma unroll
-          for (int jv = 0; jv < 4; ++jv) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(o0[jv * 8 + 0]) * inv, __uint_as_float(o0[jv * 8 + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(o0[jv * 8 + 2]) * inv, __uint_as_float(o0[jv * 8 + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(o0[jv * 8 + 4]) * inv, __uint_as_float(o0[jv * 8 + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(o0[jv * 8 + 6]) * inv, __uint_as_float(o0[jv * 8 + 7]) * inv);
-            dst[jv] = o;
+            for (int jv = 0; jv < 4; ++jv) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[jv * 8 + 0]) * inv, __uint_as_float(o[jv * 8 + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[jv * 8 + 2]) * inv, __uint_as_float(o[jv * 8 + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[jv * 8 + 4]) * inv, __uint_as_float(o[jv * 8 + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[jv * 8 + 6]) * inv, __uint_as_float(o[jv * 8 + 7]) * inv);
+              dst[jv] = w;
+            }
+          }
+        } else {
+          // ================= transposed path for the <= 16 remainder queries =================
+          // TMEM lanes are keys: block i covers keys [128 i, 128 i + 128); this warp takes blocks with i % 2 == hf.
+          const int nsp = p.n_special;
+          const int nblk = (p.tpad + QT - 1) / QT;
+          float sv[2][SPECIAL_MAX];  // logits of up to two key blocks (i = hf, hf + 2)
+          float mx[SPECIAL_MAX];
+#pragma unroll
+          for (int j = 0; j < SPECIAL_MAX; ++j) mx[j] = -INFINITY;
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii) {
+            const int i = hf + 2 * ii;
+            const int key = i * QT + r;
+            const bool blk_ok = i < nblk && i * QT + q * 32 < p.T;  // warp-uniform: any valid key in these lanes
+            if (blk_ok) {
+              uint32_t w16[16];
+              tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + 16 * i, w16);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < SPECIAL_MAX; ++j) {
+                sv[ii][j] = key < p.T ? __uint_as_float(w16[j]) : -INFINITY;
+                mx[j] = fmaxf(mx[j], sv[ii][j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < SPECIAL_MAX; ++j) sv[ii][j] = -INFINITY;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+#pragma unroll
+          for (int j = 0; j < SPECIAL_MAX; ++j)
+            if (j < nsp) {
+              const float wm = warp_max(mx[j]);
+              if (lane == 0) red_max[sw * 16 + j] = wm;
+            }
+          named_bar_sync(5, NUM_SOFTMAX_WARPS * 32);
+          float sm[SPECIAL_MAX];
+#pragma unroll
+          for (int j = 0; j < SPECIAL_MAX; ++j) {
+            sm[j] = 0.f;
+            if (j < nsp) {
+              float m = red_max[j];
+#pragma unroll
+              for (int w = 1; w < NUM_SOFTMAX_WARPS; ++w) m = fmaxf(m, red_max[w * 16 + j]);
+              const float msl = m * p.sl2;
+#pragma unroll
+              for (int ii = 0; ii < 2; ++ii) {
+                const int key = (hf + 2 * ii) * QT + r;
+                const float e = ex2(fmaf(sv[ii][j], p.sl2, -msl));  // exp2(-inf) = 0 for masked keys
+                sm[j] += e;
+                if (key < p.tpad) p3s[j * P3_STRIDE + key] = __float2bfloat16_rn(e);
+              }
+            }
           }
 #pragma unroll
-          for (int jv = 0; jv < 4; ++jv) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(o1[jv * 8 + 0]) * inv, __uint_as_float(o1[jv * 8 + 1]) * inv);
-            o.y = pack_bf16x2(__uint_as_float(o1[jv * 8 + 2]) * inv, __uint_as_float(o1[jv * 8 + 3]) * inv);
-            o.z = pack_bf16x2(__uint_as_float(o1[jv * 8 + 4]) * inv, __uint_as_float(o1[jv * 8 + 5]) * inv);
-            o.w = pack_bf16x2(__uint_as_float(o1[jv * 8 + 6]) * inv, __uint_as_float(o1[jv * 8 + 7]) * inv);
-            dst[4 + jv] = o;
+          for (int j = 0; j < SPECIAL_MAX; ++j)
+            if (j < nsp) {
+              const float ws = warp_sum(sm[j]);
+              if (lane == 0) red_sum[sw * 16 + j] = ws;
+            }
+          named_bar_sync(5, NUM_SOFTMAX_WARPS * 32);
+          // warp 4 (quarter 0, first half): lane j holds query row j -> copy its P row from smem into TMEM
+          if (sw == 0) {
+            const uint4* prow = reinterpret_cast<const uint4*>(p3s + (lane < SPECIAL_MAX ? lane : 0) * P3_STRIDE);
+            for (int c0 = 0; c0 < p.tpad; c0 += 32) {
+              if (p.tpad - c0 >= 32) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                  const uint4 u = prow[(c0 >> 3) + v4];
+                  pk[v4 * 4] = u.x; pk[v4 * 4 + 1] = u.y; pk[v4 * 4 + 2] = u.z; pk[v4 * 4 + 3] = u.w;
+                }
+                tmem_st_32x32b_x16(tmem_base + P_COL + (c0 >> 1), pk);
+              } else {
+                uint32_t pk8[8];
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4) {
+                  const uint4 u = prow[(c0 >> 3) + v4];
+                  pk8[v4 * 4] = u.x; pk8[v4 * 4 + 1] = u.y; pk8[v4 * 4 + 2] = u.z; pk8[v4 * 4 + 3] = u.w;
+                }
+                tmem_st_32x32b_x8(tmem_base + P_COL + (c0 >> 1), pk8);
+              }
+            }
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          // every chunk barrier advances one phase per tile, whichever path the tile took
+          if (lane == 0)
+            for (int c = 0; c < p.nchunks; ++c) mbar_arrive(&p_full[c]);
+          // ---- epilogue
+          mbar_wait(o_full, par);
+          tc_fence_after();
+          uint32_t o0[32], o1[32];
+          if (sw == 0) {
+            tmem_ld_32x32b_x32(tmem_base + O_COL, o0);
+            tmem_ld_32x32b_x32(tmem_base + O_COL + 32, o1);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+          if (sw == 0 && lane < nsp) {
+            float l = red_sum[lane];
+#pragma unroll
+            for (int w = 1; w < NUM_SOFTMAX_WARPS; ++w) l += red_sum[w * 16 + lane];
+            const float inv = 1.0f / l;
+            const int tok = p.n_normal * QT + lane;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * p.T + tok) * (p.H * HD) + h * HD);
+#pragma unroll
+            for (int jv = 0; jv < 4; ++jv) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o0[jv * 8 + 0]) * inv, __uint_as_float(o0[jv * 8 + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o0[jv * 8 + 2]) * inv, __uint_as_float(o0[jv * 8 + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o0[jv * 8 + 4]) * inv, __uint_as_float(o0[jv * 8 + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o0[jv * 8 + 6]) * inv, __uint_as_float(o0[jv * 8 + 7]) * inv);
+              dst[jv] = w;
+              uint4 x;
+              x.x = pack_bf16x2(__uint_as_float(o1[jv * 8 + 0]) * inv, __uint_as_float(o1[jv * 8 + 1]) * inv);
+              x.y = pack_bf16x2(__uint_as_float(o1[jv * 8 + 2]) * inv, __uint_as_float(o1[jv * 8 + 3]) * inv);
+              x.z = pack_bf16x2(__uint_as_float(o1[jv * 8 + 4]) * inv, __uint_as_float(o1[jv * 8 + 5]) * inv);
+              x.w = pack_bf16x2(__uint_as_float(o1[jv * 8 + 6]) * inv, __uint_as_float(o1[jv * 8 + 7]) * inv);
+              dst[4 + jv] = x;
+            }
           }
         }
       }
@@ -308,17 +521,19 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   const int tpad = (T + 15) / 16 * 16;
   FP_REQUIRE(tpad <= MAX_TPAD, "attention: %d tokens per image exceeds the single-pass limit of %d "
              "(crops above 224x224 need the tiled-key kernel)", T, MAX_TPAD);
-  const int nq = (T + QT - 1) / QT;
-  FP_REQUIRE(nq <= MAX_QTILES, "attention: too many query tiles");
+  const int rem = T % QT;
+  const int n_special = (rem > 0 && rem <= SPECIAL_MAX) ? rem : 0;
+  const int n_normal = T / QT + ((rem > SPECIAL_MAX) ? 1 : 0);
   const int C = 3 * H * HD;
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmQs, tmKV;
   const uint64_t rows = uint64_t(B) * T;
   if (int rc = make_tmap_2d_bf16(&tmQ, qkv, rows, uint64_t(C), uint64_t(C), QT, HD)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmQs, qkv, rows, uint64_t(C), uint64_t(C), SPECIAL_MAX, HD)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmKV, qkv, rows, uint64_t(C), uint64_t(C), uint32_t(tpad / 2), HD)) return rc;
   Params p;
   p.out = out; p.B = B; p.T = T; p.H = H;
-  p.tpad = tpad; p.nq = nq;
-  p.nchunks = (tpad + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS;
+  p.tpad = tpad; p.n_normal = n_normal; p.n_special = n_special;
+  p.nchunks = (tpad + 63) / 64;
   p.sl2 = scale * 1.4426950408889634f;
   static bool attr_done = false;
   if (!attr_done) {
@@ -328,7 +543,7 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   const int npairs = B * H;
   const int grid = npairs < sm_count() ? npairs : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
-  attention_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  attention_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQs, tmKV, p);
   FP_CUDA(cudaGetLastError());
   return 0;
 }

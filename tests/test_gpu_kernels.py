@@ -95,7 +95,7 @@ def test_gemm_epilogues(ops):
     ops.gemm(pa.to(dev), pw.to(dev), pb.to(dev), FP_EPI_PATCH_EMBED, out=tok, pos=pos.to(dev), patches_per_img=P,
              tokens_per_img=T, token_offset=5)
     ref3 = rb(rb(pa.float() @ pw.float().t() + pb.float()).view(B, P, 1024) + pos[1:].float())
-    check_stage(tok.view(B, T, 1024)[:, 5:], ref3, "patch embed")
+    check_stage(tok.view(B, T, 1024)[:, 5:], ref3, "patch embed", ulp_exact=False)  # y + pos may cancel
     assert torch.all(tok.view(B, T, 1024)[:, :5] == 0), "special-token rows must not be touched by the GEMM"
 
 
