@@ -31,8 +31,7 @@ constexpr int MAX_TPAD = 272;      // padded key count (multiple of 16)
 constexpr int ROW_BYTES = HD * 2;  // 128 B: one swizzle row
 constexpr int Q_TILE_BYTES = QT * ROW_BYTES;    // 16 KB
 constexpr int KV_BYTES = MAX_TPAD * ROW_BYTES;  // 34 KB
-constexpr int SPECIAL_MAX = 8;     // remainder rows handled by the transposed path
-constexpr int SPECIAL_N = 16;      // UMMA N (and Q rows loaded) for the transposed path: minimum for M = 128
+constexpr int SPECIAL_MAX = 16;    // remainder rows handled by the transposed path
 constexpr int NUM_SOFTMAX_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_SOFTMAX_WARPS * 32;
 constexpr int TMEM_COLS = 512;
@@ -46,7 +45,7 @@ constexpr int OFF_Q = 0;                           // 2 ring slots
 constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;    // 2 buffers
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
 constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2][128] max + [2][128] sum
-constexpr int OFF_RED = OFF_XCH + 4 * 128 * 4;     // float [8 warps][16] max + [8][16] sum (8 used)
+constexpr int OFF_RED = OFF_XCH + 4 * 128 * 4;     // float [8 warps][16] max + [8][16] sum
 constexpr int OFF_P3 = OFF_RED + 2 * 8 * 16 * 4;   // bf16 [16][P3_STRIDE]
 constexpr int OFF_BAR = OFF_P3 + SPECIAL_MAX * P3_STRIDE * 2;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -201,7 +200,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_arrive_expect_tx(&q_full[slot], Q_TILE_BYTES);
             tma_load_2d(sQ, &tmQ, &q_full[slot], h * HD, row0 + t * QT);
           } else {
-            mbar_arrive_expect_tx(&q_full[slot], SPECIAL_N * ROW_BYTES);
+            mbar_arrive_expect_tx(&q_full[slot], SPECIAL_MAX * ROW_BYTES);
             tma_load_2d(sQ, &tmQs, &q_full[slot], h * HD, row0 + p.n_normal * QT);
           }
         }
@@ -214,72 +213,65 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int n2 = p.tpad - n1;
       const uint32_t idesc_s1 = umma_idesc_bf16(QT, n1, 0, 0);
       const uint32_t idesc_s2 = umma_idesc_bf16(QT, n2 > 0 ? n2 : 16, 0, 0);
-      const uint32_t idesc_st = umma_idesc_bf16(QT, SPECIAL_N, 0, 0);    // S^T = K (M=keys) x Q_r^T (N=16)
+      const uint32_t idesc_st = umma_idesc_bf16(QT, SPECIAL_MAX, 0, 0);  // S^T = K (M=keys) x Q_r^T (N=16)
       const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);           // B (= V) is MN-major
-      const int my_pairs = (npairs - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-      const uint32_t total_tiles = uint32_t(my_pairs) * tiles_per_pair;
-      // S (or S^T) of tile n: waits for its operands and for the softmax warps to have drained S of tile n-1.
-      auto issue_scores = [&](uint32_t n) {
-        const int it = int(n / tiles_per_pair), t = int(n % tiles_per_pair);
-        const int buf = it & 1, slot = n & 1;
-        const uint32_t sK = smem_u32(smem + OFF_K + buf * KV_BYTES);
-        const uint32_t sQ = smem_u32(smem + OFF_Q + slot * Q_TILE_BYTES);
-        if (t == 0) mbar_wait(&kv_full[buf], (it >> 1) & 1);
-        mbar_wait(&q_full[slot], (n >> 1) & 1);
-        mbar_wait(s_empty, (n & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
-        if (t < p.n_normal) {  // S = Q_t K^T
-          const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
-          const uint64_t k_desc2 = umma_smem_desc_sw128(sK + 256 * ROW_BYTES, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            umma_bf16_ss(tmem_base + S_COL, q_desc + uint64_t(2 * k), k_desc1 + uint64_t(2 * k), idesc_s1, k != 0);
-            if (n2 > 0)
-              umma_bf16_ss(tmem_base + S_COL + 256, q_desc + uint64_t(2 * k), k_desc2 + uint64_t(2 * k), idesc_s2,
-                           k != 0);
-          }
-        } else {  // S^T = K Q_r^T : 128-key row blocks, 16 query columns each
-          for (int i = 0; i * QT < p.tpad; ++i) {
-            const uint64_t k_desc = umma_smem_desc_sw128(sK + uint32_t(i * QT) * ROW_BYTES, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-              umma_bf16_ss(tmem_base + S_COL + 16 * i, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), idesc_st,
-                           k != 0);
-          }
-        }
-        umma_commit(s_full);
-        umma_commit(&q_empty[slot]);
-      };
-      if (total_tiles > 0) issue_scores(0);
-      for (uint32_t n = 0; n < total_tiles; ++n) {
-        const int it = int(n / tiles_per_pair), t = int(n % tiles_per_pair);
+      uint32_t tile_iter = 0;
+      int it = 0;
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
         const int buf = it & 1;
+        const uint32_t sK = smem_u32(smem + OFF_K + buf * KV_BYTES);
         const uint32_t sV = smem_u32(smem + OFF_V + buf * KV_BYTES);
-        const bool special = t >= p.n_normal;
-        const int nwait = special ? 1 : p.nchunks;  // the transposed path publishes all of P at once
-        // ---- O = P V, P read from TMEM as the softmax warps store it
-        mbar_wait(o_empty, (n & 1) ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < p.nchunks; ++c) {
-          if (c == nwait - 1 && n + 1 < total_tiles) {
-            // the softmax warps have read all of S(n) by now (or will within one 32-key group): queue the next
-            // tile's Q K^T ahead of the last P.V chunk so that it overlaps the tail of softmax(n)
-            issue_scores(n + 1);
+        mbar_wait(&kv_full[buf], (it >> 1) & 1);
+        for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
+          const int slot = tile_iter & 1;
+          const uint32_t sQ = smem_u32(smem + OFF_Q + slot * Q_TILE_BYTES);
+          const bool special = t >= p.n_normal;
+          mbar_wait(&q_full[slot], (tile_iter >> 1) & 1);
+          mbar_wait(s_empty, (tile_iter & 1) ^ 1);
+          tc_fence_after();
+          if (!special) {
+            // ---- S = Q_t K^T
+            const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
+            const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
+            const uint64_t k_desc2 = umma_smem_desc_sw128(sK + 256 * ROW_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              umma_bf16_ss(tmem_base + S_COL, q_desc + uint64_t(2 * k), k_desc1 + uint64_t(2 * k), idesc_s1, k != 0);
+              if (n2 > 0)
+                umma_bf16_ss(tmem_base + S_COL + 256, q_desc + uint64_t(2 * k), k_desc2 + uint64_t(2 * k), idesc_s2,
+                             k != 0);
+            }
+          } else {
+            // ---- S^T = K Q_r^T : three 128-key row blocks, 16 query columns each
+            const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
+            for (int i = 0; i * QT < p.tpad; ++i) {
+              const uint64_t k_desc = umma_smem_desc_sw128(sK + uint32_t(i * QT) * ROW_BYTES, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k)
+                umma_bf16_ss(tmem_base + S_COL + 16 * i, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), idesc_st,
+                             k != 0);
+            }
           }
-          if (c < nwait) {
-            mbar_wait(&p_full[c], n & 1);
-            tc_fence_after();
+          umma_commit(s_full);
+          umma_commit(&q_empty[slot]);
+          // ---- O = P V, P read from TMEM as the softmax warps store it
+          mbar_wait(o_empty, (tile_iter & 1) ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < p.nchunks; ++c) {
+            if (!special || c == 0) {
+              mbar_wait(&p_full[c], tile_iter & 1);
+              tc_fence_after();
+            }
+            const int keys = (p.tpad - c * 64) < 64 ? (p.tpad - c * 64) : 64;
+            for (int k = 0; k < keys / 16; ++k) {
+              const int key0 = c * 64 + k * 16;
+              const uint64_t v_desc = umma_smem_desc_sw128(sV + uint32_t(key0) * ROW_BYTES, 1024, 1024);
+              umma_bf16_ts(tmem_base + O_COL, tmem_base + P_COL + uint32_t(key0 >> 1), v_desc, idesc_pv, key0 != 0);
+            }
           }
-          const int keys = (p.tpad - c * 64) < 64 ? (p.tpad - c * 64) : 64;
-          for (int k = 0; k < keys / 16; ++k) {
-            const int key0 = c * 64 + k * 16;
-            const uint64_t v_desc = umma_smem_desc_sw128(sV + uint32_t(key0) * ROW_BYTES, 1024, 1024);
-            umma_bf16_ts(tmem_base + O_COL, tmem_base + P_COL + uint32_t(key0 >> 1), v_desc, idesc_pv, key0 != 0);
-          }
+          umma_commit(o_full);
         }
-        umma_commit(o_full);
-        if (t == tiles_per_pair - 1) umma_commit(&kv_empty[buf]);
+        umma_commit(&kv_empty[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -304,50 +296,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // ---- pass 1: row max (this warp: groups with g % 2 == hf)
           float m = -INFINITY;
           if (warp_active) {
-            auto load_group = [&](int g, uint32_t (&v)[32]) {
-              const int c0 = g * 32;
-              if (p.tpad - c0 >= 32) {
-                tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
-              } else {
-                uint32_t w16[16];
-                tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
-              }
-            };
-            auto reduce_group = [&](int g, const uint32_t (&v)[32]) {
-              const int c0 = g * 32;
-              if (c0 + 32 <= p.T) m = max_group<false>(v, 32, m);
-              else                m = max_group<true>(v, p.T - c0, m);
-            };
             for (int g = hf; g < ngroups; g += 2) {
-              uint32_t va[32];
-              load_group(g, va);
-              tmem_ld_wait();
-              reduce_group(g, va);
-            }
-          }
-          xch_max[hf * 128 + r] = m;
-          named_bar_sync(1 + q, 64);
-          m = fmaxf(xch_max[r], xch_max[128 + r]);
-          const float msl = m * p.sl2;
-          // ---- pass 2: exponentials, row sum, bf16 P into TMEM (chunk c: this warp owns keys [64c + 32hf, +32)).
-          // The publication of chunk c (wait::st + fence + arrive) is deferred until chunk c+1's TMEM load is in
-          // flight, so the store latency is hidden.
-          float l = 0.f;
-          int pending = -1;
-          auto publish = [&](int c) {
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[c]);
-          };
-          for (int c = 0; c < p.nchunks; ++c) {
-            const int c0 = c * 64 + hf * 32;
-            const bool work = warp_active && c0 < p.tpad;
-            const int width = p.tpad - c0 >= 32 ? 32 : 16;
-            uint32_t v[32], pk[16];
-            if (work) {
+              const int c0 = g * 32;
+              const int width = p.tpad - c0 >= 32 ? 32 : 16;
+              uint32_t v[32];
               if (width == 32) {
                 tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
               } else {
@@ -356,16 +308,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
               }
+              tmem_ld_wait();
+              if (c0 + 32 <= p.T) m = max_group<false>(v, 32, m);
+              else                m = max_group<true>(v, p.T - c0, m);
             }
-            if (pending >= 0) publish(pending);
-            if (work) tmem_ld_wait();
-            if (c == p.nchunks - 1) {
-              // every S value this warp needs is now in registers: let the next tile's Q K^T overwrite S
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_empty);
-            }
-            if (work) {
+          }
+          xch_max[hf * 128 + r] = m;
+          named_bar_sync(1 + q, 64);
+          m = fmaxf(xch_max[r], xch_max[128 + r]);
+          const float msl = m * p.sl2;
+          // ---- pass 2: exponentials, row sum, bf16 P into TMEM (chunk c: this warp owns keys [64c + 32hf, +32))
+          float l = 0.f;
+          for (int c = 0; c < p.nchunks; ++c) {
+            const int c0 = c * 64 + hf * 32;
+            if (warp_active && c0 < p.tpad) {
+              const int width = p.tpad - c0 >= 32 ? 32 : 16;
+              uint32_t v[32], pk[16];
+              if (width == 32) {
+                tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
+              } else {
+                uint32_t w16[16];
+                tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
+              }
+              tmem_ld_wait();
               if (c0 + 32 <= p.T) l += exp_group<false>(v, p.sl2, msl, 32, pk);
               else                l += exp_group<true>(v, p.sl2, msl, p.T - c0, pk);
               if (width == 32) {
@@ -376,10 +343,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
                 tmem_st_32x32b_x8(tmem_base + lane_addr + P_COL + (c0 >> 1), pk8);
               }
+              tmem_st_wait();
             }
-            pending = c;
+            tc_fence_before();
+            __syncwarp();
+            if (c == p.nchunks - 1 && lane == 0) mbar_arrive(s_empty);  // all S reads of this warp are done
+            if (lane == 0) mbar_arrive(&p_full[c]);
           }
-          publish(pending);
           xch_sum[hf * 128 + r] = l;
           named_bar_sync(1 + q, 64);
           l = xch_sum[r] + xch_sum[128 + r];
@@ -558,7 +528,7 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   CUtensorMap tmQ, tmQs, tmKV;
   const uint64_t rows = uint64_t(B) * T;
   if (int rc = make_tmap_2d_bf16(&tmQ, qkv, rows, uint64_t(C), uint64_t(C), QT, HD)) return rc;
-  if (int rc = make_tmap_2d_bf16(&tmQs, qkv, rows, uint64_t(C), uint64_t(C), SPECIAL_N, HD)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmQs, qkv, rows, uint64_t(C), uint64_t(C), SPECIAL_MAX, HD)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmKV, qkv, rows, uint64_t(C), uint64_t(C), uint32_t(tpad / 2), HD)) return rc;
   Params p;
   p.out = out; p.B = B; p.T = T; p.H = H;
