@@ -221,3 +221,70 @@ def test_full_size_determinism_and_duplicates(lib, sd2):
     out = est.forward_mesh(crops[0], mesh, np.eye(3), np.array([0.0, 0.0, 10.0, 10.0]), 0.25, layer=2, poses=poses)
     assert int(out["top_indices"][0]) == 300
     assert out["all_scores"][517] == out["all_scores"][3]
+
+
+def test_proposals_match_reference_arithmetic(lib):
+    """Proposals (reference src/pipeline/utils.py:18-52): masked frame -> bbox_extend -> CropResizePad, against the
+    CPU restatement that is pinned to the reference class (tests/golden/crop.npz)."""
+    from freepose_b200.pipeline.proposals import Proposals
+    from oracle import crop as C
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    masks = np.zeros((2, 480, 640), dtype=bool)
+    masks[0, 100:300, 200:420] = rng.random((200, 220)) > 0.3
+    masks[1, 50:400, 30:130] = True
+    boxes = np.array([[200, 100, 419, 299], [30, 50, 129, 399]])
+    for mask_rgb in (True, False):
+        props = Proposals(img, {"boxes": torch.from_numpy(boxes), "masks": torch.from_numpy(masks)}, 224,
+                          bbox_extend=0.05, mask_rgb=mask_rgb)
+        base = np.broadcast_to((img.astype(np.float32) / 255).transpose(2, 0, 1), (2, 3, 480, 640))
+        src = base * masks[:, None] if mask_rgb else base
+        want = C.crop_resize_pad(np.ascontiguousarray(src, dtype=np.float32), boxes, 224, bbox_extend=0.05,
+                                 orig_size=(480, 640))
+        assert np.array_equal(props.proposals.cpu().numpy(), want)
+        wm = C.crop_resize_pad(np.repeat(masks[:, None], 3, 1).astype(np.float32), boxes, 224, bbox_extend=0.05,
+                               orig_size=(480, 640))[:, 0] > 0.5
+        assert np.array_equal(props.proposals_masks.cpu().numpy(), wm)
+
+
+def test_cli_extract_retrieval_features_synthetic(lib, tmp_path):
+    """scripts.extract_retrieval_features --feature ffa: (views, 1024) fp32 .npy per mesh = FFA pooling of layer-L
+    patch tokens (reference extract_retrieval_features.py:40-70)."""
+    from freepose_b200 import cli
+    from oracle import score as S
+    out = cli.run_extract_retrieval_features(["--synthetic", "2", "--synthetic_views", "6", "--synthetic_depth", "2",
+                                              "--layer", "2", "--resolution", "224", "--batch_size", "4",
+                                              "--out_dir", str(tmp_path)])
+    assert [p.name for p in out] == ["synthetic_000000.npy", "synthetic_000001.npy"]
+    arr = np.load(out[0])
+    assert arr.shape == (6, 1024) and arr.dtype == np.float32 and np.isfinite(arr).all()
+    # recompute mesh 0 through the public classes and pool with the CPU oracle
+    ds = cli.SyntheticTemplates(2, 6, 224, crop=False)
+    sample = ds[0]
+    fe = cli.DINOv2FeatureExtractor(depth=2)
+    feats = fe(sample["templates"], layer=2, feature_type="patch")
+    want, counts = S.ffa_engine_order(feats.cpu(), sample["masks"].cpu().numpy())
+    assert np.array_equal(arr, want) and counts.min() > 0
+    cls = cli.run_extract_retrieval_features(["--synthetic", "1", "--synthetic_views", "3", "--synthetic_depth", "1",
+                                              "--layer", "1", "--resolution", "224", "--feature", "cls",
+                                              "--out_dir", str(tmp_path / "cls")])
+    assert np.load(cls[0]).shape == (3, 1024)
+
+
+def test_cli_dino_inference_and_video_synthetic(lib, tmp_path):
+    import pandas as pd
+    from freepose_b200 import cli
+    common = ["--synthetic_depth", "2", "--layer", "2", "--resolution", "224", "--n_poses", "24", "--cache_size", "2"]
+    p = cli.run_dino_inference(["--synthetic", "1", "--out", str(tmp_path / "pose.csv")] + common)
+    df = pd.read_csv(p)
+    assert list(df.columns) == ["scene_id", "im_id", "obj_id", "score", "R", "t", "bbox_visib", "scale", "time"]
+    assert len(df) >= 1 and all(len(r.split()) == 9 for r in df["R"]) and all(len(t.split()) == 3 for t in df["t"])
+    tz_mm = float(df["t"][0].split()[2])
+    assert 500 < tz_mm < 10000  # millimetres, object placed 2.2-3.0 m away
+    v = cli.run_dino_inference_video(["--synthetic", "2", "--n_fine_poses", "3000", "--out", str(tmp_path / "v.csv")]
+                                     + common)
+    dv = pd.read_csv(v)
+    assert len(dv) == 2 * len(df) and (dv["time"] == -1).all()
+    assert 0.5 < float(dv["t"][0].split()[2]) < 10.0  # metres in the video CSV
+    nr = cli.run_dino_inference_video(["--synthetic", "1", "--no_rescore", "--out", str(tmp_path / "nr.csv")] + common)
+    assert len(pd.read_csv(nr)) == len(df)

@@ -98,3 +98,32 @@ def test_score_allgather_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank0-ok" in r.stdout and "rank1-ok" in r.stdout
+
+
+def test_rle_matches_the_reference_format():
+    """Uncompressed column-major RLE of the proposal JSON (reference src/pipeline/utils.py:62 ->
+    sam2.utils.amg.mask_to_rle_pytorch); the expected vectors were produced by that function."""
+    from freepose_b200.pipeline.proposals import mask_to_rle, rle_to_mask
+    m = np.array([[1, 0], [1, 1]], dtype=bool)
+    assert mask_to_rle(m) == {"size": [2, 2], "counts": [0, 2, 1, 1]}
+    m = np.zeros((3, 4), dtype=bool)
+    m[1, 2] = m[2, 2] = True
+    assert mask_to_rle(m) == {"size": [3, 4], "counts": [7, 2, 3]}
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x = rng.random((9, 7)) > 0.5
+        assert np.array_equal(rle_to_mask(mask_to_rle(x)), x)
+    assert mask_to_rle(np.zeros((2, 2), bool)) == {"size": [2, 2], "counts": [4]}
+
+
+def test_src_overlay_exposes_the_reference_names():
+    """`from src.pipeline... import X` (the imports the reference scripts use) resolve to the B200 classes."""
+    import importlib
+    for mod, name in (("src.pipeline.retrieval.dino", "DINOv2FeatureExtractor"),
+                      ("src.pipeline.retrieval.renderer", "MeshRenderer"),
+                      ("src.pipeline.estimators.pose_estimator", "DinoPoseEstimator"),
+                      ("src.pipeline.estimators.online_pose_estimator", "DinoOnlinePoseEstimator"),
+                      ("src.pipeline.utils", "Proposals"), ("src.pipeline.utils", "get_z_from_pointcloud"),
+                      ("src.utils.bbox_utils", "CropResizePad")):
+        obj = getattr(importlib.import_module(mod), name)
+        assert obj.__module__.startswith("freepose_b200."), (mod, name, obj.__module__)
