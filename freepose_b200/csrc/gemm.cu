@@ -14,6 +14,8 @@
 //   BIAS_GELU     out = bf16(gelu_erf(bf16(acc + b)))                            (mlp.fc1 + act)
 //   BIAS_LS_RES   out = bf16(res + bf16(bf16(acc + b) * gamma))                  (attn.proj / mlp.fc2 + LayerScale + residual)
 //   PATCH_EMBED   out[b*T + 1 + R + p] = bf16(bf16(acc + b) + pos[1 + p])        (patch-embed conv as GEMM + pos-embed)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -121,6 +123,78 @@ __device__ __forceinline__ f32x2 gelu2(f32x2 u) {
   return fma2(half_abs_u, erf_abs, mul2(u, splat2(0.5f)));
 }
 
+// Drains this warp's share (TMEM lane quarter q, column chunks grp, grp+G, ...) of one finished 128 x 256
+// accumulator: tcgen05.ld -> fused epilogue in packed fp32x2 -> 64-byte bf16 row segments to HBM.
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int acc, int q, int grp, int row,
+                                              int n_blk) {
+      const bool row_ok = row < p.M;
+      int out_row = row;
+      int pos_row = 0;
+      if (MODE == EPI_PATCH_EMBED) {
+        const int img = row / p.patches_per_img;
+        const int pidx = row - img * p.patches_per_img;
+        out_row = img * p.tokens_per_img + p.token_offset + pidx;
+        pos_row = 1 + pidx;
+      }
+#pragma unroll 1
+      for (int chunk = grp; chunk < BN / 32; chunk += NUM_EPI_GROUPS) {
+        const int col0 = chunk * 32;
+        const int gcol = n_blk * BN + col0;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
+        // operands that do not depend on the accumulator are fetched while the TMEM load is in flight
+        uint4 bv[4], gv[4], xv[4];
+        const uint4* bptr = reinterpret_cast<const uint4*>(p.bias + gcol);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bv[i] = __ldg(bptr + i);
+        if (MODE == EPI_BIAS_LS_RES) {
+          const uint4* gptr = reinterpret_cast<const uint4*>(p.gamma + gcol);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gv[i] = __ldg(gptr + i);
+          if (row_ok) {
+            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldo + gcol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xptr[i];
+          }
+        }
+        if (MODE == EPI_PATCH_EMBED) {
+          if (row_ok) {
+            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(pos_row) * p.N + gcol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = __ldg(xptr + i);
+          }
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+          uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
+            const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+            const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // two adjacent columns at a time in packed fp32x2
+              f32x2 v = add2(pack2(__uint_as_float(r[i * 8 + j * 2]), __uint_as_float(r[i * 8 + j * 2 + 1])),
+                             bf16x2_to_f32x2(bw[j]));
+              if (MODE == EPI_BIAS_GELU) {
+                v = gelu2(round2_bf16(v));
+              } else if (MODE == EPI_BIAS_LS_RES) {
+                v = round2_bf16(mul2(round2_bf16(v), bf16x2_to_f32x2(gw[j])));
+                v = add2(v, bf16x2_to_f32x2(xw[j]));
+              } else if (MODE == EPI_PATCH_EMBED) {
+                v = add2(round2_bf16(v), bf16x2_to_f32x2(xw[j]));
+              }
+              ow[j] = f32x2_to_bf16x2(v);
+            }
+            optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -217,73 +291,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      int out_row = row;
-      int pos_row = 0;
-      if (MODE == EPI_PATCH_EMBED) {
-        const int img = row / p.patches_per_img;
-        const int pidx = row - img * p.patches_per_img;
-        out_row = img * p.tokens_per_img + p.token_offset + pidx;
-        pos_row = 1 + pidx;
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = grp; chunk < BN / 32; chunk += NUM_EPI_GROUPS) {
-        const int col0 = chunk * 32;
-        const int gcol = n_blk * BN + col0;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
-        // operands that do not depend on the accumulator are fetched while the TMEM load is in flight
-        uint4 bv[4], gv[4], xv[4];
-        const uint4* bptr = reinterpret_cast<const uint4*>(p.bias + gcol);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bv[i] = __ldg(bptr + i);
-        if (MODE == EPI_BIAS_LS_RES) {
-          const uint4* gptr = reinterpret_cast<const uint4*>(p.gamma + gcol);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) gv[i] = __ldg(gptr + i);
-          if (row_ok) {
-            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldo + gcol);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = xptr[i];
-          }
-        }
-        if (MODE == EPI_PATCH_EMBED) {
-          if (row_ok) {
-            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(pos_row) * p.N + gcol);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = __ldg(xptr + i);
-          }
-        }
-        tmem_ld_wait();
-        if (row_ok) {
-          uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
-            const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
-            const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // two adjacent columns at a time in packed fp32x2
-              f32x2 v = add2(pack2(__uint_as_float(r[i * 8 + j * 2]), __uint_as_float(r[i * 8 + j * 2 + 1])),
-                             bf16x2_to_f32x2(bw[j]));
-              if (MODE == EPI_BIAS_GELU) {
-                v = gelu2(round2_bf16(v));
-              } else if (MODE == EPI_BIAS_LS_RES) {
-                v = round2_bf16(mul2(round2_bf16(v), bf16x2_to_f32x2(gw[j])));
-                v = add2(v, bf16x2_to_f32x2(xw[j]));
-              } else if (MODE == EPI_PATCH_EMBED) {
-                v = add2(round2_bf16(v), bf16x2_to_f32x2(xw[j]));
-              }
-              ow[j] = f32x2_to_bf16x2(v);
-            }
-            optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
-        }
-      }
+      epilogue_tile<MODE>(p, tmem_base, acc, q, grp, row, n_blk);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -296,6 +306,140 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): the two CTAs of a cluster drive ONE 256 x 256 tcgen05.mma.  Each CTA stages its own
+// 128 rows of A and 128 of the 256 W rows per K slab (32 KB/stage instead of 48 KB: 6 stages, and half the operand
+// traffic per SM), the leader CTA issues the MMAs, each CTA drains the 128 accumulator rows that live in its own
+// TMEM.  Barriers: `full` lives in the leader (both CTAs' TMA bytes land on it); `empty` and `tfull` exist in both
+// CTAs and are signalled by multicast tcgen05.commit; `tempty` lives in the leader and is arrived on remotely.
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = 2 * BM * BK * 2;  // A half (16 KB) + W half (16 KB)
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES2]  (leader's copy is the live one)
+  uint64_t* empty_bar = bars + STAGES2;            // [STAGES2]
+  uint64_t* tfull_bar = bars + 2 * STAGES2;        // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES2 + 2;   // [2]        (leader's copy is the live one)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  constexpr int BM2 = 2 * BM;
+  const int num_m_tiles = (p.M + BM2 - 1) / BM2;
+  const int num_n_tiles = p.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int kblocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  if (warp == 2) tmem_alloc_2cta(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // both CTAs' bytes
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sA = smem + stage * STAGE2_BYTES;
+          uint8_t* sB = sA + BM * BK * 2;
+          tma_load_2d_2cta(sA, &tmA, leader_full, kb * BK, m_blk * BM2 + int(rank) * BM);
+          tma_load_2d_2cta(sB, &tmB, leader_full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM2, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint64_t a_desc = umma_smem_desc_sw128(sA, 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(sA + BM * BK * 2, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2cta(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage], 0b11);  // frees this smem slot in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull_bar[acc], 0b11);  // accumulator (both halves) complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (each CTA drains its 128 rows)
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
+      const int row = m_blk * BM2 + int(rank) * BM + q * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<MODE>(p, tmem_base, acc, q, grp, row, n_blk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling barriers / reading operands that live in this CTA
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+static int prof_kind(int mode, int K) {
+  return mode == EPI_PATCH_EMBED ? PROF_GEMM_PATCH
+         : mode == EPI_BIAS_GELU ? PROF_GEMM_FC1
+         : mode == EPI_BIAS      ? PROF_GEMM_QKV
+         : (K > 1024 ? PROF_GEMM_FC2 : PROF_GEMM_PROJ);
+}
+
 template <int MODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
   static bool attr_done = false;
@@ -305,12 +449,23 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cuda
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  const int kind = MODE == EPI_PATCH_EMBED ? PROF_GEMM_PATCH
-                   : MODE == EPI_BIAS_GELU ? PROF_GEMM_FC1
-                   : MODE == EPI_BIAS      ? PROF_GEMM_QKV
-                   : (p.K > 1024 ? PROF_GEMM_FC2 : PROF_GEMM_PROJ);
-  ProfScope prof(kind, 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
+  ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
   gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int MODE>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    FP_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
+  const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
+  gemm2_kernel<MODE><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, p);
   FP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -323,9 +478,12 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   FP_REQUIRE(a.K % BK == 0, "gemm: K=%d must be a multiple of %d", a.K, BK);
   FP_REQUIRE(a.A && a.W && a.out && a.bias, "gemm: null operand");
   FP_REQUIRE(a.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+  // large problems: 2-CTA clusters (256 x 256 tiles); small ones (e.g. the single query crop): 1-CTA 128 x 256 tiles
+  static const int force = [] { const char* e = getenv("FP_GEMM_CTAS"); return e ? atoi(e) : 0; }();
+  const bool two = force ? force == 2 : a.M >= 2048;
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_2d_bf16(&tmA, a.A, uint64_t(a.M), uint64_t(a.K), uint64_t(a.lda), BM, BK)) return rc;
-  if (int rc = make_tmap_2d_bf16(&tmB, a.W, uint64_t(a.N), uint64_t(a.K), uint64_t(a.K), BN, BK)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmB, a.W, uint64_t(a.N), uint64_t(a.K), uint64_t(a.K), two ? BN / 2 : BN, BK)) return rc;
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.out = a.out; p.ldo = a.ldo;
@@ -334,14 +492,15 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.tokens_per_img = a.tokens_per_img;
   p.token_offset = a.token_offset;
   switch (a.mode) {
-    case EPI_BIAS: return launch<EPI_BIAS>(tmA, tmB, p, stream);
-    case EPI_BIAS_GELU: return launch<EPI_BIAS_GELU>(tmA, tmB, p, stream);
+    case EPI_BIAS: return two ? launch2<EPI_BIAS>(tmA, tmB, p, stream) : launch<EPI_BIAS>(tmA, tmB, p, stream);
+    case EPI_BIAS_GELU:
+      return two ? launch2<EPI_BIAS_GELU>(tmA, tmB, p, stream) : launch<EPI_BIAS_GELU>(tmA, tmB, p, stream);
     case EPI_BIAS_LS_RES:
       FP_REQUIRE(a.gamma && a.res, "gemm: LayerScale/residual epilogue needs gamma and res");
-      return launch<EPI_BIAS_LS_RES>(tmA, tmB, p, stream);
+      return two ? launch2<EPI_BIAS_LS_RES>(tmA, tmB, p, stream) : launch<EPI_BIAS_LS_RES>(tmA, tmB, p, stream);
     case EPI_PATCH_EMBED:
       FP_REQUIRE(a.res && a.tokens_per_img > 0, "gemm: patch-embed epilogue needs pos-embed and token layout");
-      return launch<EPI_PATCH_EMBED>(tmA, tmB, p, stream);
+      return two ? launch2<EPI_PATCH_EMBED>(tmA, tmB, p, stream) : launch<EPI_PATCH_EMBED>(tmA, tmB, p, stream);
   }
   set_error("gemm: unknown epilogue mode %d", a.mode);
   return -1;
