@@ -132,4 +132,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t row_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  FP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  FP_REQUIRE((row_stride_elems * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", int(r));
+  return 0;
+}
+
 }  // namespace fp

@@ -147,6 +147,18 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       "l"(policy)
       : "memory");
 }
+// 2D tile store shared -> global (bulk async group); rows/cols outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all previously committed bulk stores of this thread have finished READING their smem source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // L2 eviction policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
@@ -200,8 +212,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with RELAXED semantics: the only thing being published is "my tcgen05.ld's have completed" (ordered by
+// tcgen05.fence::before_thread_sync); a .release at cluster scope would make ptxas emit MEMBAR.ALL.GPU + ERRBAR, i.e.
+// wait for every outstanding global store of the epilogue on every tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr,
@@ -302,5 +317,8 @@ __device__ __forceinline__ uint32_t elect_one() {
 // 2D row-major bf16 tensor [rows, cols] (cols contiguous), box = [box_cols, box_rows], 128B swizzle.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// Same with a 32-column (64-byte) box and 64-byte swizzle: the output staging tiles of the GEMM epilogue.
+int make_tmap_2d_bf16_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t row_stride_elems, uint32_t box_rows);
 
 }  // namespace fp

@@ -34,7 +34,11 @@ constexpr int NUM_EPI_GROUPS = 3;                   // warps per TMEM lane quart
 constexpr int NUM_EPI_WARPS = 4 * NUM_EPI_GROUPS;   // 12: three per SM sub-partition hide the epilogue's ALU/MUFU latency
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2 * 3 * 64;  // per warp: bias + gamma for its <= 3 column chunks
+constexpr int OUT_STAGE_BYTES = NUM_EPI_WARPS * 32 * 64;     // per warp: one 32-row x 32-column bf16 output tile (TMA store source)
+// layout after the operand ring: [barriers 256 B][bias/gamma staging][pad to 512 B][output staging]
+constexpr int OUT_STAGE_OFF = (256 + EPI_STAGE_BYTES + 511) / 512 * 512;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + OUT_STAGE_OFF + OUT_STAGE_BYTES;
 
 struct Params {
   int M, N, K;
@@ -46,6 +50,7 @@ struct Params {
   int patches_per_img;
   int tokens_per_img;
   int token_offset;
+  int debug;  // perf experiments only: 1 = skip epilogue stores, 2 = always load tile (0,0)
 };
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per issue slot) -------------------
@@ -123,81 +128,135 @@ __device__ __forceinline__ f32x2 gelu2(f32x2 u) {
   return fma2(half_abs_u, erf_abs, mul2(u, splat2(0.5f)));
 }
 
+// Per-tile operands that do not depend on the accumulator are fetched BEFORE the wait on the accumulator barrier,
+// so their global-memory latency is hidden: bias (+ LayerScale gamma) of this warp's column chunks go to a
+// warp-private smem staging area (read back as broadcast LDS), the first chunk's residual / pos-embed row segment
+// goes to registers.
+struct EpiPrefetch {
+  uint4 x[4];  // residual (BIAS_LS_RES) or pos-embed (PATCH_EMBED) of the first chunk
+};
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_prefetch(const Params& p, uint4* stage, int grp, int lane, int row, int n_blk,
+                                                  EpiPrefetch& pf) {
+  // lanes 0..11: bias (3 chunks x 4 x 16 B), lanes 12..23: gamma
+  const int which = lane / 12, l12 = lane - which * 12;
+  const int ci = l12 >> 2, part = l12 & 3;
+  const int chunk = grp + ci * NUM_EPI_GROUPS;
+  if (lane < (MODE == EPI_BIAS_LS_RES ? 24 : 12) && chunk < BN / 32) {
+    const bf16* src = (which == 0 ? p.bias : p.gamma) + n_blk * BN + chunk * 32 + part * 8;
+    stage[which * 12 + l12] = __ldg(reinterpret_cast<const uint4*>(src));
+  }
+  if (MODE == EPI_BIAS_LS_RES || MODE == EPI_PATCH_EMBED) {
+    const int gcol = n_blk * BN + grp * 32;
+    if (row < p.M) {
+      const bf16* src;
+      if (MODE == EPI_BIAS_LS_RES) {
+        src = p.res + size_t(row) * p.ldo + gcol;
+      } else {
+        const int img = row / p.patches_per_img;
+        src = p.res + size_t(1 + row - img * p.patches_per_img) * p.N + gcol;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pf.x[i] = reinterpret_cast<const uint4*>(src)[i];
+    }
+  }
+  __syncwarp();
+}
+
 // Drains this warp's share (TMEM lane quarter q, column chunks grp, grp+G, ...) of one finished 128 x 256
 // accumulator: tcgen05.ld -> fused epilogue in packed fp32x2 -> 64-byte bf16 row segments to HBM.
 template <int MODE>
-__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int acc, int q, int grp, int row,
-                                              int n_blk) {
-      const bool row_ok = row < p.M;
-      int out_row = row;
-      int pos_row = 0;
-      if (MODE == EPI_PATCH_EMBED) {
-        const int img = row / p.patches_per_img;
-        const int pidx = row - img * p.patches_per_img;
-        out_row = img * p.tokens_per_img + p.token_offset + pidx;
-        pos_row = 1 + pidx;
-      }
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmOut, uint32_t tmem_base, int acc,
+                                              int q, int grp, int row, int n_blk, const uint4* stage, EpiPrefetch& pf,
+                                              uint8_t* out_stage) {
+  // Contiguous-row outputs go through a swizzled smem tile and a TMA bulk store (full 32-byte sectors, asynchronous,
+  // rows past M clipped by the hardware); the patch-embed scatter keeps direct stores (rows are remapped per image).
+  constexpr bool kTmaStore = MODE != EPI_PATCH_EMBED;
+  const int lane = threadIdx.x & 31;
+  const bool row_ok = row < p.M;
+  int out_row = row;
+  int pos_row = 0;
+  if (MODE == EPI_PATCH_EMBED) {
+    const int img = row / p.patches_per_img;
+    const int pidx = row - img * p.patches_per_img;
+    out_row = img * p.tokens_per_img + p.token_offset + pidx;
+    pos_row = 1 + pidx;
+  }
+  int ci = 0;
 #pragma unroll 1
-      for (int chunk = grp; chunk < BN / 32; chunk += NUM_EPI_GROUPS) {
-        const int col0 = chunk * 32;
-        const int gcol = n_blk * BN + col0;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
-        // operands that do not depend on the accumulator are fetched while the TMEM load is in flight
-        uint4 bv[4], gv[4], xv[4];
-        const uint4* bptr = reinterpret_cast<const uint4*>(p.bias + gcol);
+  for (int chunk = grp; chunk < BN / 32; chunk += NUM_EPI_GROUPS, ++ci) {
+    const int col0 = chunk * 32;
+    const int gcol = n_blk * BN + col0;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
+    uint4 bv[4], gv[4], xv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bv[i] = __ldg(bptr + i);
-        if (MODE == EPI_BIAS_LS_RES) {
-          const uint4* gptr = reinterpret_cast<const uint4*>(p.gamma + gcol);
+    for (int i = 0; i < 4; ++i) {
+      bv[i] = stage[ci * 4 + i];
+      if (MODE == EPI_BIAS_LS_RES) gv[i] = stage[12 + ci * 4 + i];
+      if (MODE == EPI_BIAS_LS_RES || MODE == EPI_PATCH_EMBED) xv[i] = pf.x[i];
+    }
+    // residual / pos-embed of the NEXT chunk: in flight while this chunk is computed
+    if ((MODE == EPI_BIAS_LS_RES || MODE == EPI_PATCH_EMBED) && row_ok && chunk + NUM_EPI_GROUPS < BN / 32) {
+      const int ncol = gcol + NUM_EPI_GROUPS * 32;
+      const bf16* src = MODE == EPI_BIAS_LS_RES ? p.res + size_t(row) * p.ldo + ncol : p.res + size_t(pos_row) * p.N + ncol;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gv[i] = __ldg(gptr + i);
-          if (row_ok) {
-            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(row) * p.ldo + gcol);
+      for (int i = 0; i < 4; ++i) pf.x[i] = reinterpret_cast<const uint4*>(src)[i];
+    }
+    tmem_ld_wait();
+    if (kTmaStore) {
+      // the previous chunk's bulk store must have finished reading the staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
+    if (kTmaStore || row_ok) {
+      uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = xptr[i];
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
+        const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+        const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // two adjacent columns at a time in packed fp32x2
+          f32x2 v = add2(pack2(__uint_as_float(r[i * 8 + j * 2]), __uint_as_float(r[i * 8 + j * 2 + 1])),
+                         bf16x2_to_f32x2(bw[j]));
+          if (MODE == EPI_BIAS_GELU) {
+            v = gelu2(round2_bf16(v));
+          } else if (MODE == EPI_BIAS_LS_RES) {
+            v = round2_bf16(mul2(round2_bf16(v), bf16x2_to_f32x2(gw[j])));
+            v = add2(v, bf16x2_to_f32x2(xw[j]));
+          } else if (MODE == EPI_PATCH_EMBED) {
+            v = add2(round2_bf16(v), bf16x2_to_f32x2(xw[j]));
           }
+          ow[j] = f32x2_to_bf16x2(v);
         }
-        if (MODE == EPI_PATCH_EMBED) {
-          if (row_ok) {
-            const uint4* xptr = reinterpret_cast<const uint4*>(p.res + size_t(pos_row) * p.N + gcol);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = __ldg(xptr + i);
-          }
-        }
-        tmem_ld_wait();
-        if (row_ok) {
-          uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
-            const uint32_t gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
-            const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-            uint32_t ow[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // two adjacent columns at a time in packed fp32x2
-              f32x2 v = add2(pack2(__uint_as_float(r[i * 8 + j * 2]), __uint_as_float(r[i * 8 + j * 2 + 1])),
-                             bf16x2_to_f32x2(bw[j]));
-              if (MODE == EPI_BIAS_GELU) {
-                v = gelu2(round2_bf16(v));
-              } else if (MODE == EPI_BIAS_LS_RES) {
-                v = round2_bf16(mul2(round2_bf16(v), bf16x2_to_f32x2(gw[j])));
-                v = add2(v, bf16x2_to_f32x2(xw[j]));
-              } else if (MODE == EPI_PATCH_EMBED) {
-                v = add2(round2_bf16(v), bf16x2_to_f32x2(xw[j]));
-              }
-              ow[j] = f32x2_to_bf16x2(v);
-            }
-            optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          }
+        if (kTmaStore) {
+          // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
+          *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        } else {
+          optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
+    }
+    if (kTmaStore) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && p.debug != 1) {
+        tma_store_2d(tmOut, out_stage, gcol, row - lane);  // box = 32 rows of this warp's lane quarter x 32 columns
+        tma_store_commit();
+      }
+    }
+  }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmOut, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -286,14 +345,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int grp = (warp - 4) >> 2;   // 0..NUM_EPI_GROUPS-1: which column chunks of the tile this warp drains
+    uint4* epi_stage = reinterpret_cast<uint4*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256) + (warp - 4) * 24;
+    uint8_t* out_stage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + OUT_STAGE_OFF + (warp - 4) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + q * 32 + lane;
+      EpiPrefetch pf;
+      epilogue_prefetch<MODE>(p, epi_stage, grp, lane, row, n_blk, pf);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<MODE>(p, tmem_base, acc, q, grp, row, n_blk);
+      epilogue_tile<MODE>(p, &tmOut, tmem_base, acc, q, grp, row, n_blk, epi_stage, pf, out_stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -301,6 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if (warp >= 4 && lane == 0) tma_store_wait_all();  // smem staging must outlive the bulk stores reading it
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -315,11 +379,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------
 constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = 2 * BM * BK * 2;  // A half (16 KB) + W half (16 KB)
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + OUT_STAGE_OFF + OUT_STAGE_BYTES;
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
@@ -375,8 +440,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
           uint8_t* sA = smem + stage * STAGE2_BYTES;
           uint8_t* sB = sA + BM * BK * 2;
-          tma_load_2d_2cta(sA, &tmA, leader_full, kb * BK, m_blk * BM2 + int(rank) * BM);
-          tma_load_2d_2cta(sB, &tmB, leader_full, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          const int mrow = p.debug == 2 ? int(rank) * BM : m_blk * BM2 + int(rank) * BM;
+          const int nrow = p.debug == 2 ? int(rank) * (BN / 2) : n_blk * BN + int(rank) * (BN / 2);
+          tma_load_2d_2cta(sA, &tmA, leader_full, p.debug == 2 ? 0 : kb * BK, mrow);
+          tma_load_2d_2cta(sB, &tmB, leader_full, p.debug == 2 ? 0 : kb * BK, nrow);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
@@ -413,14 +480,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------------ epilogue (each CTA drains its 128 rows)
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
+    uint4* epi_stage = reinterpret_cast<uint4*>(smem + STAGES2 * STAGE2_BYTES + 256) + (warp - 4) * 24;
+    uint8_t* out_stage = smem + STAGES2 * STAGE2_BYTES + OUT_STAGE_OFF + (warp - 4) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM2 + int(rank) * BM + q * 32 + lane;
+      EpiPrefetch pf;
+      epilogue_prefetch<MODE>(p, epi_stage, grp, lane, row, n_blk, pf);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<MODE>(p, tmem_base, acc, q, grp, row, n_blk);
+      epilogue_tile<MODE>(p, &tmOut, tmem_base, acc, q, grp, row, n_blk, epi_stage, pf, out_stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
@@ -428,6 +499,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+  if (warp >= 4 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   cluster_sync_all();  // the peer may still be signalling barriers / reading operands that live in this CTA
   if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
@@ -441,7 +513,8 @@ static int prof_kind(int mode, int K) {
 }
 
 template <int MODE>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
+           cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     FP_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -450,13 +523,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cuda
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
-  gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmOut, p);
   FP_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int MODE>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cudaStream_t stream) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
+            cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     FP_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -465,7 +539,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, cud
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
   const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
-  gemm2_kernel<MODE><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, p);
+  gemm2_kernel<MODE><<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB, tmOut, p);
   FP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -484,6 +558,12 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_2d_bf16(&tmA, a.A, uint64_t(a.M), uint64_t(a.K), uint64_t(a.lda), BM, BK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmB, a.W, uint64_t(a.N), uint64_t(a.K), uint64_t(a.K), two ? BN / 2 : BN, BK)) return rc;
+  CUtensorMap tmOut;
+  {
+    // store map over the output rows this GEMM may write (patch-embed scatters with direct stores instead)
+    const uint64_t out_rows = a.mode == EPI_PATCH_EMBED ? 32 : uint64_t(a.M);
+    if (int rc = make_tmap_2d_bf16_sw64(&tmOut, a.out, out_rows, uint64_t(a.N), uint64_t(a.ldo), 32)) return rc;
+  }
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.out = a.out; p.ldo = a.ldo;
@@ -491,16 +571,18 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.patches_per_img = a.patches_per_img > 0 ? a.patches_per_img : 1;
   p.tokens_per_img = a.tokens_per_img;
   p.token_offset = a.token_offset;
+  static const int dbg = [] { const char* e = getenv("FP_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
   switch (a.mode) {
-    case EPI_BIAS: return two ? launch2<EPI_BIAS>(tmA, tmB, p, stream) : launch<EPI_BIAS>(tmA, tmB, p, stream);
+    case EPI_BIAS: return two ? launch2<EPI_BIAS>(tmA, tmB, tmOut, p, stream) : launch<EPI_BIAS>(tmA, tmB, tmOut, p, stream);
     case EPI_BIAS_GELU:
-      return two ? launch2<EPI_BIAS_GELU>(tmA, tmB, p, stream) : launch<EPI_BIAS_GELU>(tmA, tmB, p, stream);
+      return two ? launch2<EPI_BIAS_GELU>(tmA, tmB, tmOut, p, stream) : launch<EPI_BIAS_GELU>(tmA, tmB, tmOut, p, stream);
     case EPI_BIAS_LS_RES:
       FP_REQUIRE(a.gamma && a.res, "gemm: LayerScale/residual epilogue needs gamma and res");
-      return two ? launch2<EPI_BIAS_LS_RES>(tmA, tmB, p, stream) : launch<EPI_BIAS_LS_RES>(tmA, tmB, p, stream);
+      return two ? launch2<EPI_BIAS_LS_RES>(tmA, tmB, tmOut, p, stream) : launch<EPI_BIAS_LS_RES>(tmA, tmB, tmOut, p, stream);
     case EPI_PATCH_EMBED:
       FP_REQUIRE(a.res && a.tokens_per_img > 0, "gemm: patch-embed epilogue needs pos-embed and token layout");
-      return two ? launch2<EPI_PATCH_EMBED>(tmA, tmB, p, stream) : launch<EPI_PATCH_EMBED>(tmA, tmB, p, stream);
+      return two ? launch2<EPI_PATCH_EMBED>(tmA, tmB, tmOut, p, stream) : launch<EPI_PATCH_EMBED>(tmA, tmB, tmOut, p, stream);
   }
   set_error("gemm: unknown epilogue mode %d", a.mode);
   return -1;
