@@ -108,24 +108,28 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
 //   gelu(u) = u/2 + |u|/2 * erf(|u|/sqrt2),   erf(a) = 1 - (a1 t + ... + a5 t^5) exp(-a^2),  t = 1/(1 + p a)
 // ~11.5 issue slots per element instead of ~39 for libdevice erff (the fc1 epilogue has to fit under the MMA time).
 __device__ __forceinline__ f32x2 gelu2(f32x2 u) {
-  const f32x2 z = mul2(u, splat2(0.70710678118654752f));
-  float z0, z1;
-  unpack2(z, z0, z1);
-  const f32x2 az = pack2(fabsf(z0), fabsf(z1));
+  // y = u * sqrt(log2 e / 2)  =>  exp(-(u/sqrt2)^2) = exp2(-y^2);  |u/sqrt2| = |y| / sqrt(log2 e)
+  constexpr float kS = 0.84932180028801904f;             // sqrt(log2(e) / 2)
+  constexpr float kP = 0.3275911f / 1.2011224087864498f;  // A&S p, rescaled to |y|
+  const f32x2 y = mul2(u, splat2(kS));
+  float y0, y1;
+  unpack2(y, y0, y1);
+  const f32x2 ay = pack2(fabsf(y0), fabsf(y1));
   float d0, d1;
-  unpack2(fma2(az, splat2(0.3275911f), splat2(1.0f)), d0, d1);
+  unpack2(fma2(ay, splat2(kP), splat2(1.0f)), d0, d1);
   const f32x2 t = pack2(rcp_fast(d0), rcp_fast(d1));
-  f32x2 pl = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
-  pl = fma2(pl, t, splat2(1.421413741f));
-  pl = fma2(pl, t, splat2(-0.284496736f));
-  pl = fma2(pl, t, splat2(0.254829592f));
+  // -(a1 t + ... + a5 t^5): coefficients negated so that erf(|z|) = fma(poly, e, 1)
+  f32x2 pl = fma2(t, splat2(-1.061405429f), splat2(1.453152027f));
+  pl = fma2(pl, t, splat2(-1.421413741f));
+  pl = fma2(pl, t, splat2(0.284496736f));
+  pl = fma2(pl, t, splat2(-0.254829592f));
   pl = mul2(pl, t);
   float e0, e1;
-  unpack2(mul2(mul2(z, z), splat2(-1.4426950408889634f)), e0, e1);
-  const f32x2 e = pack2(ex2_fast(e0), ex2_fast(e1));
-  const f32x2 erf_abs = fma2(mul2(pl, splat2(-1.0f)), e, splat2(1.0f));  // erf(|z|)
-  const f32x2 half_abs_u = mul2(az, splat2(0.70710678118654752f));       // |u| / 2
-  return fma2(half_abs_u, erf_abs, mul2(u, splat2(0.5f)));
+  unpack2(mul2(y, y), e0, e1);
+  const f32x2 e = pack2(ex2_fast(-e0), ex2_fast(-e1));   // the negation folds into the MUFU operand
+  const f32x2 erf_abs = fma2(pl, e, splat2(1.0f));       // erf(|u| / sqrt2)
+  // gelu(u) = u/2 + |u|/2 * erf(|u|/sqrt2) = (y + |y| * erf_abs) / (2 kS)
+  return mul2(fma2(ay, erf_abs, y), splat2(0.5f / kS));
 }
 
 // Per-tile operands that do not depend on the accumulator are fetched BEFORE the wait on the accumulator barrier,
@@ -205,13 +209,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
       for (int i = 0; i < 4; ++i) pf.x[i] = reinterpret_cast<const uint4*>(src)[i];
     }
     tmem_ld_wait();
-    if (kTmaStore) {
-      // the previous chunk's bulk store must have finished reading the staging tile
-      if (lane == 0) tma_store_wait_read();
-      __syncwarp();
-    }
+    uint4 outv[4];
     if (kTmaStore || row_ok) {
-      uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t bw[4] = {bv[i].x, bv[i].y, bv[i].z, bv[i].w};
@@ -233,14 +232,21 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
           }
           ow[j] = f32x2_to_bf16x2(v);
         }
-        if (kTmaStore) {
-          // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
-          *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
-              make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        } else {
-          optr[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        }
+        outv[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
+    }
+    if (kTmaStore) {
+      // only now must the previous chunk's bulk store have finished reading the staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = outv[i];
+    } else if (row_ok) {
+      uint4* optr = reinterpret_cast<uint4*>(p.out + size_t(out_row) * p.ldo + gcol);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) optr[i] = outv[i];
     }
     if (kTmaStore) {
       fence_proxy_async_smem();
