@@ -18,6 +18,9 @@
 //
 // Arithmetic contract = flash/xformers attention (oracle/vit.py contract_attention): logits and softmax statistics
 // in fp32, un-normalised P rounded to bf16 before P.V (fp32 accumulate), one rounding of O.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -49,8 +52,8 @@ constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
 constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2][128] max + [2][128] sum
 constexpr int OFF_TQ = OFF_XCH + 4 * 128 * 4;      // tail Q rows: 2 slots x 16 rows x 128 B (TMA, 128B swizzle)
 constexpr int OFF_TQF = OFF_TQ + 2 * TAIL_BOX * ROW_BYTES;   // float [8][64]: tail queries in fp32
-constexpr int OFF_TP = OFF_TQF + TAIL_MAX * HD * 4;          // float [272][8]: bf16-rounded P of the tail rows
-constexpr int OFF_TO = OFF_TP + MAX_TPAD * TAIL_MAX * 4;     // float [4 warps][8][64]: partial P.V
+constexpr int OFF_TP = OFF_TQF + TAIL_MAX * HD * 4;          // float2 [272][8]: bf16-rounded P of the tail rows, duplicated (p, p)
+constexpr int OFF_TO = OFF_TP + MAX_TPAD * TAIL_MAX * 8;     // float [4 warps][8][64]: partial P.V
 constexpr int OFF_TRED = OFF_TO + NUM_TAIL_WARPS * TAIL_MAX * HD * 4;  // float [2][4][8]: max / sum partials
 constexpr int OFF_BAR = OFF_TRED + 2 * NUM_TAIL_WARPS * TAIL_MAX * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -63,12 +66,43 @@ struct Params {
   int n_tail;     // remainder query rows (<= 8) handled by the tail warps, 0 if none
   int nchunks;    // 64-key chunks
   float sl2;      // scale * log2(e)
+  int debug_skip_tail;
+  long long* dbg;  // perf experiments: per-phase cycle counters of the tail warps (nullptr = off)
 };
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+// D (16x8, fp32) += A (16x16 bf16, row) * B (16x8 bf16, col); used only for the <= 8 tail query rows
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -135,7 +169,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
                  const __grid_constant__ CUtensorMap tmKV, const bf16* __restrict__ qkv_unused, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array keeps the shared address space: LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]  MMA commit (+ the four tail warps when there are tail rows)
@@ -366,124 +401,120 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp >= 4 + NUM_SOFTMAX_WARPS && p.n_tail > 0) {
-    // ---------------------------------------------------------------------------- tail queries on the CUDA cores
-    // 128 threads.  Phase 1: thread <-> key (keys tt, tt+128, tt+256): logits of the <= 8 tail queries against its
-    // keys, K rows read from the TMA-swizzled smem tile (row-per-thread reads are conflict free under the 128B
-    // swizzle).  Phase 2: softmax statistics across keys (shuffles + smem).  Phase 3: lane <-> two head dims, warp
-    // <-> every 4th key: O += P[key] * V[key]; partials combined through smem.
+    // ---------------------------------------------------------------------------- tail queries (<= 8 rows)
+    // Warp-level mma.sync.m16n8k16 on the K/V tiles already in shared memory (ldmatrix understands the TMA 128B
+    // swizzle: every 8x8 sub-matrix row is one 16-byte chunk).  Keys are dealt to the four warps in blocks of 16;
+    // the logit accumulators of two 8-key tiles are exactly the A fragment of the following P.V step, so P never
+    // leaves registers.  Only rows 0..7 of the 16-row fragments carry queries (rows 8..15 are ignored).
     const int tw = warp - 4 - NUM_SOFTMAX_WARPS;   // 0..3
     const int tt = tw * 32 + lane;                 // 0..127
     const int nt = p.n_tail;
-    float* tqf = reinterpret_cast<float*>(smem + OFF_TQF);     // [8][64]
-    float* tp = reinterpret_cast<float*>(smem + OFF_TP);       // [272][8]
-    float* to = reinterpret_cast<float*>(smem + OFF_TO);       // [4][8][64]
+    const int g = lane >> 2, tq = lane & 3;        // fragment row group / thread-in-group
+    float* to = reinterpret_cast<float*>(smem + OFF_TO);       // [4 warps][8 rows][64]
     float* tredm = reinterpret_cast<float*>(smem + OFF_TRED);  // [4][8]
     float* treds = tredm + NUM_TAIL_WARPS * TAIL_MAX;          // [4][8]
+    const int nblk16 = p.tpad / 16;                // 16-key blocks, dealt round-robin to the warps
     int it = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
       const int b = pair / p.H, h = pair - b * p.H;
       const int buf = it & 1;
-      const uint8_t* sK = smem + OFF_K + buf * KV_BYTES;
-      const uint8_t* sV = smem + OFF_V + buf * KV_BYTES;
-      const uint8_t* sTQ = smem + OFF_TQ + buf * TAIL_BOX * ROW_BYTES;
+      const uint32_t sK = smem_u32(smem + OFF_K + buf * KV_BYTES);
+      const uint32_t sV = smem_u32(smem + OFF_V + buf * KV_BYTES);
+      const uint32_t sTQ = smem_u32(smem + OFF_TQ + buf * TAIL_BOX * ROW_BYTES);
       mbar_wait(&kv_full[buf], (it >> 1) & 1);
       mbar_wait(&tq_full[buf], (it >> 1) & 1);
-      // tail queries -> fp32 (so the inner loop needs no unpacking on the query side)
-      for (int i = tt; i < nt * HD / 2; i += NUM_TAIL_WARPS * 32) {
-        const int j = i / (HD / 2), dp = i - j * (HD / 2);  // query row, pair of head dims
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(sTQ + j * ROW_BYTES + (((dp >> 2) ^ (j & 7)) << 4) + (dp & 3) * 4);
-        tqf[j * HD + 2 * dp] = bf16lo(u);
-        tqf[j * HD + 2 * dp + 1] = bf16hi(u);
+      if (p.debug_skip_tail) {  // perf experiment: handshakes only
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&kv_empty[buf]); mbar_arrive(&tq_empty[buf]); }
+        continue;
       }
-      named_bar_sync(6, NUM_TAIL_WARPS * 32);
-      // ---- phase 1: logits
-      float s[3][TAIL_MAX];
+      // ---- A fragments of the tail queries: 16 rows x 64 dims = 4 k-steps x {a0..a3}
+      uint32_t qa[4][4];
 #pragma unroll
-      for (int kk = 0; kk < 3; ++kk)
+      for (int ks = 0; ks < 4; ++ks) {
+        // ldmatrix.x4: matrices (rows 0-7, dims 16ks..+7), (rows 8-15, same dims), (rows 0-7, dims +8..), (rows 8-15, +8..)
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int chunk = 2 * ks + (lane >> 4);
+        ldmatrix_x4(sTQ + row * ROW_BYTES + ((chunk ^ (row & 7)) << 4), qa[ks]);
+      }
+      // ---- logits for this warp's key blocks: sacc[blk][tile][4]
+      constexpr int MAXB = 5;  // ceil(17 / 4)
+      float sacc[MAXB][2][4];
+      float mrow = -INFINITY;  // max over this thread's logits of row g (rows >= nt are ignored later)
 #pragma unroll
-        for (int j = 0; j < TAIL_MAX; ++j) s[kk][j] = 0.f;
-      const int nkk = (tt + 256 < p.T) ? 3 : ((tt + 128 < p.T) ? 2 : (tt < p.T ? 1 : 0));
-      for (int c = 0; c < 8; ++c) {  // 16-byte chunks of a 128-byte row = 8 head dims
-        float kf[3][8];
+      for (int bi = 0; bi < MAXB; ++bi) {
+        const int blk = tw + bi * NUM_TAIL_WARPS;
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          const int key = tt + 128 * kk;
-          if (kk < nkk) {
-            const uint4 u = *reinterpret_cast<const uint4*>(sK + key * ROW_BYTES + ((c ^ (key & 7)) << 4));
-            kf[kk][0] = bf16lo(u.x); kf[kk][1] = bf16hi(u.x); kf[kk][2] = bf16lo(u.y); kf[kk][3] = bf16hi(u.y);
-            kf[kk][4] = bf16lo(u.z); kf[kk][5] = bf16hi(u.z); kf[kk][6] = bf16lo(u.w); kf[kk][7] = bf16hi(u.w);
-          } else {
+        for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) kf[kk][e] = 0.f;
+          for (int e = 0; e < 4; ++e) sacc[bi][tile][e] = 0.f;
+        if (blk < nblk16) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            // B fragments (K^T): ldmatrix.x4 -> tile0 {b0,b1}, tile1 {b0,b1}; key row = blk*16 + tile*8 + (lane&7)
+            uint32_t kb[4];
+            const int key = blk * 16 + ((lane >> 4) << 3) + (lane & 7);
+            const int chunk = 2 * ks + ((lane >> 3) & 1);
+            ldmatrix_x4(sK + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), kb);
+            mma_bf16_16816(sacc[bi][0], qa[ks], kb[0], kb[1]);
+            mma_bf16_16816(sacc[bi][1], qa[ks], kb[2], kb[3]);
+          }
+#pragma unroll
+          for (int tile = 0; tile < 2; ++tile) {
+            const int k0 = blk * 16 + tile * 8 + 2 * tq;  // keys of c0, c1
+            if (k0 < p.T) mrow = fmaxf(mrow, sacc[bi][tile][0]);
+            if (k0 + 1 < p.T) mrow = fmaxf(mrow, sacc[bi][tile][1]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < TAIL_MAX; ++j)
-          if (j < nt) {
-            const float4 qa = *reinterpret_cast<const float4*>(tqf + j * HD + c * 8);
-            const float4 qb = *reinterpret_cast<const float4*>(tqf + j * HD + c * 8 + 4);
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              float a = s[kk][j];
-              a = fmaf(qa.x, kf[kk][0], a); a = fmaf(qa.y, kf[kk][1], a);
-              a = fmaf(qa.z, kf[kk][2], a); a = fmaf(qa.w, kf[kk][3], a);
-              a = fmaf(qb.x, kf[kk][4], a); a = fmaf(qb.y, kf[kk][5], a);
-              a = fmaf(qb.z, kf[kk][6], a); a = fmaf(qb.w, kf[kk][7], a);
-              s[kk][j] = a;
-            }
-          }
       }
-      // ---- phase 2: softmax statistics over all keys
-#pragma unroll
-      for (int j = 0; j < TAIL_MAX; ++j)
-        if (j < nt) {
-          float m = -INFINITY;
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk)
-            if (kk < nkk) m = fmaxf(m, s[kk][j]);
-          m = warp_max(m);
-          if (lane == 0) tredm[tw * TAIL_MAX + j] = m;
-        }
+      mrow = fmaxf(mrow, __shfl_xor_sync(0xffffffffu, mrow, 1));
+      mrow = fmaxf(mrow, __shfl_xor_sync(0xffffffffu, mrow, 2));
+      if (tq == 0) tredm[tw * TAIL_MAX + g] = mrow;
       named_bar_sync(6, NUM_TAIL_WARPS * 32);
-      float lsum[TAIL_MAX];
+      const float m = fmaxf(fmaxf(tredm[g], tredm[TAIL_MAX + g]), fmaxf(tredm[2 * TAIL_MAX + g], tredm[3 * TAIL_MAX + g]));
+      const float msl = m * p.sl2;
+      // ---- P = exp2(...), row sums, O partial = P V with P straight from the accumulator registers
+      float oacc[8][4];
 #pragma unroll
-      for (int j = 0; j < TAIL_MAX; ++j) {
-        lsum[j] = 0.f;
-        if (j < nt) {
-          const float m = fmaxf(fmaxf(tredm[j], tredm[TAIL_MAX + j]), fmaxf(tredm[2 * TAIL_MAX + j], tredm[3 * TAIL_MAX + j]));
-          const float msl = m * p.sl2;
+      for (int nd = 0; nd < 8; ++nd)
 #pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            const int key = tt + 128 * kk;
-            const float e = kk < nkk ? ex2(fmaf(s[kk][j], p.sl2, -msl)) : 0.f;
-            lsum[j] += e;
-            if (key < p.tpad) tp[key * TAIL_MAX + j] = bf16_round(e);  // P is rounded to bf16 before P.V
+        for (int e = 0; e < 4; ++e) oacc[nd][e] = 0.f;
+      float lsum = 0.f;
+#pragma unroll
+      for (int bi = 0; bi < MAXB; ++bi) {
+        const int blk = tw + bi * NUM_TAIL_WARPS;
+        if (blk < nblk16) {
+          uint32_t pa[4];
+#pragma unroll
+          for (int tile = 0; tile < 2; ++tile) {
+            const int k0 = blk * 16 + tile * 8 + 2 * tq;
+            const float e0 = k0 < p.T ? ex2(fmaf(sacc[bi][tile][0], p.sl2, -msl)) : 0.f;
+            const float e1 = k0 + 1 < p.T ? ex2(fmaf(sacc[bi][tile][1], p.sl2, -msl)) : 0.f;
+            lsum += e0 + e1;
+            pa[2 * tile] = pack_bf16x2(e0, e1);   // rows g     (a0 / a2)
+            pa[2 * tile + 1] = 0u;                // rows g + 8 (a1 / a3): unused query rows
           }
-          const float ws = warp_sum(lsum[j]);
-          if (lane == 0) treds[tw * TAIL_MAX + j] = ws;
+#pragma unroll
+          for (int nd2 = 0; nd2 < 4; ++nd2) {
+            // V as B operand (k = keys, n = dims): ldmatrix.x4.trans -> dims tile 2*nd2 {b0,b1}, tile 2*nd2+1 {b0,b1}
+            uint32_t vb[4];
+            const int key = blk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int chunk = 2 * nd2 + (lane >> 4);
+            ldmatrix_x4_trans(sV + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), vb);
+            mma_bf16_16816(oacc[2 * nd2], pa, vb[0], vb[1]);
+            mma_bf16_16816(oacc[2 * nd2 + 1], pa, vb[2], vb[3]);
+          }
         }
-      }
-      named_bar_sync(6, NUM_TAIL_WARPS * 32);
-      // ---- phase 3: O = P V   (lane <-> head dims 2*lane, 2*lane+1; warp <-> keys tw, tw+4, ...)
-      float ox[TAIL_MAX], oy[TAIL_MAX];
-#pragma unroll
-      for (int j = 0; j < TAIL_MAX; ++j) { ox[j] = 0.f; oy[j] = 0.f; }
-      for (int key = tw; key < p.T; key += NUM_TAIL_WARPS) {
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(sV + key * ROW_BYTES + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4);
-        const float vx = bf16lo(u), vy = bf16hi(u);
-        const float4 pa = *reinterpret_cast<const float4*>(tp + key * TAIL_MAX);
-        const float4 pb = *reinterpret_cast<const float4*>(tp + key * TAIL_MAX + 4);
-        const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-        for (int j = 0; j < TAIL_MAX; ++j)
-          if (j < nt) { ox[j] = fmaf(pj[j], vx, ox[j]); oy[j] = fmaf(pj[j], vy, oy[j]); }
       }
       // K, V and the tail Q rows of this pair are no longer needed by these warps
       __syncwarp();
       if (lane == 0) { mbar_arrive(&kv_empty[buf]); mbar_arrive(&tq_empty[buf]); }
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+      if (tq == 0) treds[tw * TAIL_MAX + g] = lsum;
 #pragma unroll
-      for (int j = 0; j < TAIL_MAX; ++j)
-        if (j < nt) *reinterpret_cast<float2*>(to + (tw * TAIL_MAX + j) * HD + 2 * lane) = make_float2(ox[j], oy[j]);
+      for (int nd = 0; nd < 8; ++nd)  // rows g (c0, c1) only; dims nd*8 + 2*tq
+        *reinterpret_cast<float2*>(to + (tw * TAIL_MAX + g) * HD + nd * 8 + 2 * tq) = make_float2(oacc[nd][0], oacc[nd][1]);
       named_bar_sync(6, NUM_TAIL_WARPS * 32);
       for (int i = tt; i < nt * HD / 2; i += NUM_TAIL_WARPS * 32) {
         const int j = i / (HD / 2), dp = i - j * (HD / 2);
@@ -527,6 +558,9 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   Params p;
   p.out = out; p.B = B; p.T = T; p.H = H;
   p.tpad = tpad; p.n_normal = n_normal; p.n_tail = n_tail;
+  if (getenv("FP_ATTN_NOTAIL")) p.n_tail = 0;
+  p.debug_skip_tail = getenv("FP_ATTN_SKIPTAIL") ? 1 : 0;
+  p.dbg = nullptr;  // perf experiment: skips the tail rows (wrong results)
   p.nchunks = (tpad + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS;
   p.sl2 = scale * 1.4426950408889634f;
   static bool attr_done = false;
