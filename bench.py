@@ -209,8 +209,7 @@ def run_b200(args):
         """One proposal: everything on the device; host_io adds the H2D of the query and the D2H of the result."""
         if host_io:
             query = query.to(dev, non_blocking=True)
-        feats, depth, _ = est.render_features(mesh, None, layer=args.layer)
-        qf = est.feature_extractor(query[None], layer=args.layer, feature_type="patch")
+        feats, depth, _, qf = est.render_features(mesh, None, layer=args.layer, query=query)  # 520 renders + query
         _, idx, vals, _ = ops.score_topk(feats, qf, k=3, scores_out=sg.local_view(rank))
         all_scores = sg.gather(rank)                       # ONE all-gather of per-hypothesis scores (no-op at N=1)
         ext = ops.depth_extents(depth, K_t, view_idx=idx)

@@ -54,10 +54,12 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int = 16, scale
     return out
 
 
-def im2col(image: torch.Tensor):
+def im2col(image: torch.Tensor, out: torch.Tensor | None = None):
     B, _, res, _ = image.shape
     g = res // 14
-    out = torch.empty(B * g * g, KPAD, dtype=bf16, device=image.device)
+    if out is None:
+        out = torch.empty(B * g * g, KPAD, dtype=bf16, device=image.device)
+    assert out.dtype == bf16 and out.is_contiguous() and out.shape == (B * g * g, KPAD)
     is_f32 = image.dtype == torch.float32
     assert is_f32 or image.dtype == bf16
     check(load().fp_im2col_patches(ptr(image), int(is_f32), ptr(out), B, res, KPAD, stream_ptr()),
@@ -195,8 +197,10 @@ def norm_lut(device) -> torch.Tensor:
     return _norm_lut_dev[key]
 
 
-def crop_resize_pad(src: torch.Tensor, boxes: torch.Tensor, target: int, to_patches: bool = False):
-    """CropResizePad gather.  src: u8 (B,H,W,3) or fp32 (B,3,H,W); boxes (B,4) int32 xyxy (exclusive)."""
+def crop_resize_pad(src: torch.Tensor, boxes: torch.Tensor, target: int, to_patches: bool = False,
+                    out: torch.Tensor | None = None):
+    """CropResizePad gather.  src: u8 (B,H,W,3) or fp32 (B,3,H,W); boxes (B,4) int32 xyxy (exclusive).
+    `out` (patch-matrix mode): a preallocated (>= B*g*g, 640) bf16 buffer whose first rows are written."""
     dev = src.device
     B = src.shape[0]
     u8 = src.dtype == torch.uint8
@@ -204,7 +208,11 @@ def crop_resize_pad(src: torch.Tensor, boxes: torch.Tensor, target: int, to_patc
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     if to_patches:
         g = target // 14
-        dst = torch.empty(B * g * g, KPAD, dtype=bf16, device=dev)
+        if out is not None:
+            assert out.dtype == bf16 and out.is_contiguous() and out.shape[1] == KPAD and out.shape[0] >= B * g * g
+            dst = out
+        else:
+            dst = torch.empty(B * g * g, KPAD, dtype=bf16, device=dev)
     else:
         dst = torch.empty(B, 3, target, target, dtype=torch.float32, device=dev)
     boxes = boxes.to(torch.int32).contiguous()

@@ -120,13 +120,25 @@ class DinoPoseEstimator(nn.Module):
 
     # ---------------------------------------------------------------- B200-native hot path
     @torch.inference_mode()
-    def render_features(self, mesh, poses=None, layer=22, resolution=None):
+    def render_features(self, mesh, poses=None, layer=22, resolution=None, query=None):
         """raster -> mask bbox -> CropResizePad -> patch matrix -> ViT.  Returns (feats (B,P,1024) bf16,
-        depth (B,res,res) fp32, crop status)."""
+        depth (B,res,res) fp32, crop status[, query feats (1,P,1024)]).
+
+        `query` ((3,T,T) float crop in [0,1]): its patch rows are appended to the same patch matrix so that the
+        hypotheses and the query go through ONE batched ViT forward (the reference runs the query as a separate
+        batch of one, pose_estimator.py:84; the arithmetic per image is identical)."""
         rgb, depth = self.renderer.render_device(mesh, poses)
         T = resolution or self.renderer.resolution
-        patches, _, _, status = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
+        B, P = rgb.shape[0], (T // 14) ** 2
+        n_img = B + (1 if query is not None else 0)
+        patches = torch.empty(n_img * P, ops.KPAD, dtype=bf16, device=self.device)
+        _, _, _, status = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches)
+        if query is not None:
+            q = query.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            ops.im2col(q[None], out=patches[B * P:])
         feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+        if query is not None:
+            return feats[:B], depth, status, feats[B:]
         return feats, depth, status
 
     @torch.inference_mode()
@@ -134,8 +146,7 @@ class DinoPoseEstimator(nn.Module):
         """Render-and-compare of one proposal against all hypotheses of `mesh` (already at rendering scale).
         Same outputs as ``forward`` (without 'retrieved_proposals')."""
         pose_list = self.mesh_poses if poses is None else list(poses)
-        feats, depth, _ = self.render_features(mesh, poses, layer=layer)
-        query_feat = self.feature_extractor(proposal[None], layer=layer, feature_type="patch")
+        feats, depth, _, query_feat = self.render_features(mesh, poses, layer=layer, query=proposal)
         scores, top_idx, top_val, _ = ops.score_topk(feats, query_feat, k=k)
         r = self.renderer.resolution
         K_t = np.array([[self.renderer.focal, 0, r / 2], [0, self.renderer.focal, r / 2], [0, 0, 1]])

@@ -41,14 +41,14 @@ class MeshRenderer:
         return ops.rasterize(v, f, c, P, self.focal, self.focal, r / 2, r / 2, r, msaa=self.msaa,
                              cull_backfaces=cull_faces)
 
-    def proposals_device(self, rgb, depth, resolution=None, to_patches=True):
+    def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None):
         """Device version of generate_proposals: mask -> bbox -> CropResizePad.  Returns
         (patch matrix | fp32 crops, bbox (B,4) int32, masks u8 (B,res,res))."""
         res = rgb.shape[1]
         T = resolution or res
         lo, hi = (105, 315) if res == 420 else (res // 4, res - res // 4)  # renderer.py:117 is hard-coded for 420
         bbox, count, mask = ops.mask_bbox(depth, fallback=(lo, hi), min_count=100, return_mask=True)
-        out, status = ops.crop_resize_pad(rgb, bbox, T, to_patches=to_patches)
+        out, status = ops.crop_resize_pad(rgb, bbox, T, to_patches=to_patches, out=out)
         return out, bbox, mask, status
 
     # ------------------------------------------------------------------ reference-shaped API (host results)
