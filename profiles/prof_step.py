@@ -20,8 +20,7 @@ mesh = synthetic_mesh(0, subdivisions=5)
 est = DinoPoseEstimator(n_poses=hyp, cache_size=0, cache_dir="/tmp/fp_prof_cache", weights=sd, resolution=224, chunk=hyp + 1)
 query = torch.rand(3, 224, 224, device="cuda")
 for _ in range(steps):
-    feats, depth, _ = est.render_features(mesh, None, layer=layers)
-    qf = est.feature_extractor(query[None], layer=layers, feature_type="patch")
+    feats, depth, _, qf = est.render_features(mesh, None, layer=layers, query=query)  # as bench.py does
     ops.score_topk(feats, qf, k=3)
 torch.cuda.synchronize()
 print("done")
