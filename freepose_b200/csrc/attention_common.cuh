@@ -1,0 +1,107 @@
+// Device helpers shared by the attention kernels (attention.cu: all keys of a head resident, T <= 272;
+// attention_long.cu: tiled keys with online softmax for larger crops).
+#pragma once
+
+#include "common.cuh"
+
+namespace fp {
+namespace attn {
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+// D (16x8, fp32) += A (16x16 bf16, row) * B (16x8 bf16, col); used only for the <= 8 tail query rows
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// exponentials of 32 logits -> 16 packed bf16x2 words; returns the fp32 sum of the unrounded values.
+// MASKED: columns >= valid are forced to 0 (only the group that straddles T takes this path).
+template <bool MASKED>
+__device__ __forceinline__ float exp_group(const uint32_t (&v)[32], float sl2, float msl, int valid,
+                                           uint32_t (&packed)[16]) {
+  float part[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains instead of one 32-long dependency
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float e0 = ex2(fmaf(__uint_as_float(v[j]), sl2, -msl));
+    float e1 = ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -msl));
+    if (MASKED) {
+      e0 = j < valid ? e0 : 0.f;
+      e1 = j + 1 < valid ? e1 : 0.f;
+    }
+    part[(j >> 1) & 3] += e0 + e1;
+    packed[j >> 1] = pack_bf16x2(e0, e1);
+  }
+  return (part[0] + part[1]) + (part[2] + part[3]);
+}
+
+template <bool MASKED>
+__device__ __forceinline__ float max_group(const uint32_t (&v)[32], int valid, float m) {
+  float part[4] = {m, m, m, m};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = (!MASKED || j < valid) ? __uint_as_float(v[j]) : -INFINITY;
+    part[j & 3] = fmaxf(part[j & 3], x);
+  }
+  return fmaxf(fmaxf(part[0], part[1]), fmaxf(part[2], part[3]));
+}
+
+
+}  // namespace attn
+}  // namespace fp

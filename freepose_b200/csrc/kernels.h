@@ -36,7 +36,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------- attention
 // qkv: [B*T, 3*H*64] bf16 (q | k | v, head-major inside each), out: [B*T, H*64] bf16.
+// T <= 272 (crops up to 224^2): all keys of a head resident in TMEM, one softmax pass.  Above that the call is routed
+// to attention_long_bf16: key blocks of 256 with an online softmax (oracle: contract_attention(key_block=256)).
 int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
+int attention_long_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------- elementwise
 // y = bf16(((x - mean) * rstd) * w + b), fp32 two-pass statistics, rows of D = 1024.

@@ -130,14 +130,39 @@ def contract_layernorm(x, w, b, eps):
     return rb((xc * rstd) * w + b)
 
 
-def contract_attention(q, k, v, scale):
-    """Flash/xformers-style attention on bf16-valued fp32 tensors (B, H, N, hd)."""
-    s = (q @ k.transpose(-2, -1)) * scale            # fp32 logits, never rounded
-    m = s.amax(dim=-1, keepdim=True)
-    p = torch.exp(s - m)                              # fp32
-    l = p.sum(dim=-1, keepdim=True)                   # row sum of the UNROUNDED p
-    o = (rb(p) @ v) / l                               # P rounded to bf16 for the tensor-core P.V
-    return rb(o)
+SINGLE_PASS_KEYS = 272   # padded keys the single-pass kernel holds in TMEM (freepose_b200/csrc/attention.cu)
+KEY_BLOCK = 256          # key block of the tiled-key kernel (freepose_b200/csrc/attention_long.cu)
+
+
+def contract_attention(q, k, v, scale, key_block=None):
+    """Flash/xformers-style attention on bf16-valued fp32 tensors (B, H, N, hd).
+
+    Up to SINGLE_PASS_KEYS keys the softmax is a single pass; above that (crops larger than 224^2) it is the
+    block-wise online softmax of flash attention with KEY_BLOCK keys per block: the bf16 P of block b is taken
+    against the running max after block b, and O / l are rescaled by exp(m_old - m_new) between blocks.
+    """
+    N = k.shape[-2]
+    if key_block is None:
+        key_block = KEY_BLOCK if (N + 15) // 16 * 16 > SINGLE_PASS_KEYS else 0
+    if not key_block or N <= key_block:
+        s = (q @ k.transpose(-2, -1)) * scale            # fp32 logits, never rounded
+        m = s.amax(dim=-1, keepdim=True)
+        p = torch.exp(s - m)                              # fp32
+        l = p.sum(dim=-1, keepdim=True)                   # row sum of the UNROUNDED p
+        o = (rb(p) @ v) / l                               # P rounded to bf16 for the tensor-core P.V
+        return rb(o)
+    m = torch.full(q.shape[:-1] + (1,), float("-inf"), dtype=q.dtype)
+    l = torch.zeros_like(m)
+    o = torch.zeros_like(q)
+    for k0 in range(0, N, key_block):
+        s = (q @ k[..., k0:k0 + key_block, :].transpose(-2, -1)) * scale
+        m_new = torch.maximum(m, s.amax(dim=-1, keepdim=True))
+        alpha = torch.exp(m - m_new)                      # 0 for the first block
+        p = torch.exp(s - m_new)
+        l = l * alpha + p.sum(dim=-1, keepdim=True)
+        o = o * alpha + rb(p) @ v[..., k0:k0 + key_block, :]
+        m = m_new
+    return rb(o / l)
 
 
 class _PatchEmbed(nn.Module):

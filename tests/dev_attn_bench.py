@@ -1,7 +1,7 @@
 import sys, torch
 sys.path.insert(0, ".")
 from freepose_b200 import ops
-B = 521
+B = int(__import__("os").environ.get("ATTN_B", "521"))
 for T in ([int(a) for a in sys.argv[1:]] or [261]):
     qkv = torch.randn(B*T, 3072, device="cuda").to(torch.bfloat16)
     for _ in range(3): ops.attention(qkv,B,T)

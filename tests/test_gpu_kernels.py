@@ -129,9 +129,30 @@ def test_attention(ops, B, T):
     check_stage(out, ref, f"attention B={B} T={T}", ulp_exact=False)
 
 
-def test_attention_rejects_long_sequences(ops):
-    with pytest.raises(RuntimeError, match="single-pass limit"):
-        ops.attention(torch.zeros(905, 3072, dtype=bf, device=dev), 1, 905)
+@pytest.mark.parametrize("B,T", [(2, 905), (1, 273), (3, 512), (1, 529), (2, 1029), (1, 400)])
+def test_attention_tiled_keys(ops, B, T):
+    """Crops above 224^2 (905 tokens = the reference's 420^2 crops): key blocks of 256 with an online softmax."""
+    from oracle.vit import contract_attention
+    torch.manual_seed(T)
+    qkv = torch.randn(B * T, 3072).to(bf)
+    out = ops.attention(qkv.to(dev), B, T)
+    q, k, v = qkv.float().view(B, T, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    ref = contract_attention(q, k, v, 0.125).transpose(1, 2).reshape(B * T, 1024)
+    check_stage(out, ref, f"attention (tiled keys) B={B} T={T}", ulp_exact=False)
+
+
+def test_attention_tiled_keys_growing_max(ops):
+    """Keys ordered so that the running max rises in every block: the O rescale path carries all the weight."""
+    from oracle.vit import contract_attention
+    torch.manual_seed(11)
+    B, T = 1, 905
+    qkv = torch.randn(B * T, 3, 16, 64)
+    qkv[:, 1] *= torch.linspace(0.5, 6.0, T).view(T, 1, 1)              # later keys give larger logits
+    qkv = qkv.reshape(B * T, 3072).to(bf)
+    out = ops.attention(qkv.to(dev), B, T)
+    q, k, v = qkv.float().view(B, T, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    ref = contract_attention(q, k, v, 0.125).transpose(1, 2).reshape(B * T, 1024)
+    check_stage(out, ref, "attention (tiled keys) growing max", ulp_exact=False)
 
 
 def test_attention_sharp_softmax(ops):

@@ -62,6 +62,28 @@ def test_vit_tokens_and_each_block_vs_oracle(engine2, sd2):
     assert torch.equal(engine2.forward(imgs[4:5].to(dev), layer=2, feature_type="all")[0], allt[4])  # batch invariance
 
 
+def test_vit_reference_native_420_crops(engine2, sd2):
+    """The reference's own crop size (dino_inference.py: 420^2 -> 900 patches + 5 = 905 tokens): interpolated pos-embed,
+    the tiled-key attention kernel, and ragged GEMM rows (2 x 905)."""
+    from oracle.pipeline import reference_normalize
+    from oracle.vit import OracleViT
+    torch.manual_seed(1)
+    img = torch.rand(2, 3, 420, 420)
+    oc = OracleViT(sd2, contract=True)
+    with torch.no_grad():
+        xn = reference_normalize(img.to(bf)).float()
+        t0 = oc.prepare_tokens_with_masks(xn)
+        t1 = oc.blocks[0](t0)
+        t2 = oc.blocks[1](t1)
+    e0 = engine2.forward(img.to(dev), layer=0, feature_type="all")
+    assert e0.shape == (2, 905, 1024)
+    assert rel_l2(e0, oc.norm(t0)) < 1e-3
+    assert rel_l2(engine2.forward(img.to(dev), layer=1, feature_type="all"), oc.norm(t1)) < REL_BLOCK
+    e2 = engine2.forward(img.to(dev), layer=2, feature_type="patch")
+    assert e2.shape == (2, 900, 1024)
+    assert rel_l2(e2, oc.norm(t2)[:, 5:]) < 2 * REL_BLOCK
+
+
 def test_vit_full_depth_22_vs_oracle(lib):
     """One 224^2 crop through all 22 blocks (the reference's layer) against the contract oracle, the eager-bf16
     oracle and fp32 ground truth."""
