@@ -51,9 +51,9 @@ constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;    // 2 buffers
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
 constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2][128] max + [2][128] sum
 constexpr int OFF_TQ = OFF_XCH + 4 * 128 * 4;      // tail Q rows: 2 slots x 16 rows x 128 B (TMA, 128B swizzle)
-constexpr int OFF_TQF = OFF_TQ + 2 * TAIL_BOX * ROW_BYTES;   // float [8][64]: tail queries in fp32
-constexpr int OFF_TP = OFF_TQF + TAIL_MAX * HD * 4;          // float2 [272][8]: bf16-rounded P of the tail rows, duplicated (p, p)
-constexpr int OFF_TO = OFF_TP + MAX_TPAD * TAIL_MAX * 8;     // float [4 warps][8][64]: partial P.V
+constexpr int OFF_OST = OFF_TQ + 2 * TAIL_BOX * ROW_BYTES;   // output staging: 8 softmax warps x (32 rows x 64 B), 64B swizzle
+constexpr int OFF_TO = OFF_OST + NUM_SOFTMAX_WARPS * 2048;   // float [4 warps][8][64]: partial P.V of the tail rows
+static_assert(OFF_OST % 1024 == 0, "TMA store staging must keep the swizzle alignment");
 constexpr int OFF_TRED = OFF_TO + NUM_TAIL_WARPS * TAIL_MAX * HD * 4;  // float [2][4][8]: max / sum partials
 constexpr int OFF_BAR = OFF_TRED + 2 * NUM_TAIL_WARPS * TAIL_MAX * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -66,15 +66,17 @@ struct Params {
   int n_tail;     // remainder query rows (<= 8) handled by the tail warps, 0 if none
   int nchunks;    // 64-key chunks
   float sl2;      // scale * log2(e)
-  int debug_skip_tail;
   long long* dbg;  // perf experiments: per-phase cycle counters of the tail warps (nullptr = off)
 };
 
 using namespace attn;
 
+// T_CONST: token count known at compile time (261 = the 224^2 crops of the headline path: every chunk width, mask and
+// trip count folds to a constant and the straddling-group code is emitted once); 0 = any T <= 272 at run time.
+template <bool TIMING, int T_CONST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
-                 const __grid_constant__ CUtensorMap tmKV, const bf16* __restrict__ qkv_unused, const Params p) {
+                 const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmOut, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the __shared__ array keeps the shared address space: LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -96,19 +98,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = p.B * p.H;
-  const int half_rows = p.tpad / 2;
-  const int tiles_per_pair = p.n_normal;
-  (void)qkv_unused;
+  constexpr int kRem = T_CONST % QT;
+  const int T = T_CONST ? T_CONST : p.T;
+  const int tpad = T_CONST ? (T_CONST + 15) / 16 * 16 : p.tpad;
+  const int n_tail = T_CONST ? ((kRem > 0 && kRem <= TAIL_MAX) ? kRem : 0) : p.n_tail;
+  const int tiles_per_pair = T_CONST ? (T_CONST / QT + (kRem > TAIL_MAX ? 1 : 0)) : p.n_normal;
+  const int nchunks = T_CONST ? ((T_CONST + 15) / 16 * 16 + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS : p.nchunks;
+  constexpr bool kAllRowsLive = T_CONST != 0 && (kRem == 0 || kRem <= TAIL_MAX);  // no partially filled full tile
+  const int half_rows = tpad / 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmQt);
     tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], (tiles_per_pair > 0 ? 1 : 0) + (p.n_tail > 0 ? NUM_TAIL_WARPS : 0));
+      mbar_init(&kv_empty[i], (tiles_per_pair > 0 ? 1 : 0) + (n_tail > 0 ? NUM_TAIL_WARPS : 0));
       mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
       mbar_init(&tq_full[i], 1); mbar_init(&tq_empty[i], NUM_TAIL_WARPS);
     }
@@ -130,10 +138,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t qi = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
         const int b = pair / p.H, h = pair - b * p.H;
-        const int row0 = b * p.T;
+        const int row0 = b * T;
         const int buf = it & 1;
         mbar_wait(&kv_empty[buf], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[buf], 2 * p.tpad * ROW_BYTES);
+        mbar_arrive_expect_tx(&kv_full[buf], 2 * tpad * ROW_BYTES);
         uint8_t* sK = smem + OFF_K + buf * KV_BYTES;
         uint8_t* sV = smem + OFF_V + buf * KV_BYTES;
         const int kcol = p.H * HD + h * HD, vcol = 2 * p.H * HD + h * HD;
@@ -141,10 +149,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_2d(sK + half_rows * ROW_BYTES, &tmKV, &kv_full[buf], kcol, row0 + half_rows);
         tma_load_2d(sV, &tmKV, &kv_full[buf], vcol, row0);
         tma_load_2d(sV + half_rows * ROW_BYTES, &tmKV, &kv_full[buf], vcol, row0 + half_rows);
-        if (p.n_tail > 0) {
+        if (n_tail > 0) {
           mbar_wait(&tq_empty[buf], ((it >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&tq_full[buf], TAIL_BOX * ROW_BYTES);
-          tma_load_2d(smem + OFF_TQ + buf * TAIL_BOX * ROW_BYTES, &tmQt, &tq_full[buf], h * HD, row0 + p.T - p.n_tail);
+          tma_load_2d(smem + OFF_TQ + buf * TAIL_BOX * ROW_BYTES, &tmQt, &tq_full[buf], h * HD, row0 + T - n_tail);
         }
         for (int t = 0; t < tiles_per_pair; ++t, ++qi) {
           const int slot = qi & 1;
@@ -157,8 +165,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------- MMA issuer
     if (lane == 0 && tiles_per_pair > 0) {
-      const int n1 = p.tpad > 256 ? 256 : p.tpad;
-      const int n2 = p.tpad - n1;
+      const int n1 = tpad > 256 ? 256 : tpad;
+      const int n2 = tpad - n1;
       const uint32_t idesc_s1 = umma_idesc_bf16(QT, n1, 0, 0);
       const uint32_t idesc_s2 = umma_idesc_bf16(QT, n2 > 0 ? n2 : 16, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);  // B (= V) is MN-major
@@ -172,9 +180,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
           const int slot = tile_iter & 1;
           const uint32_t sQ = smem_u32(smem + OFF_Q + slot * Q_TILE_BYTES);
+          const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0;
+          long long tm0 = 0, tm1 = 0, tm2 = 0, tm3 = 0, tm4 = 0, tm5 = 0;
+          if (timing) tm0 = clock64();
           mbar_wait(&q_full[slot], (tile_iter >> 1) & 1);
+          if (timing) tm1 = clock64();
           mbar_wait(s_empty, (tile_iter & 1) ^ 1);
           tc_fence_after();
+          if (timing) tm2 = clock64();
           // ---- S = Q_t K^T
           const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
           const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
@@ -189,12 +202,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_commit(s_full);
           umma_commit(&q_empty[slot]);
           // ---- O = P V, P read from TMEM as the softmax warps store it, chunk by chunk
+          if (timing) tm3 = clock64();
           mbar_wait(o_empty, (tile_iter & 1) ^ 1);
           tc_fence_after();
-          for (int c = 0; c < p.nchunks; ++c) {
+          if (timing) tm4 = clock64();
+          for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&p_full[c], tile_iter & 1);
             tc_fence_after();
-            const int keys = (p.tpad - c * 64) < 64 ? (p.tpad - c * 64) : 64;
+            const int keys = (tpad - c * 64) < 64 ? (tpad - c * 64) : 64;
             for (int k = 0; k < keys / 16; ++k) {
               const int key0 = c * 64 + k * 16;
               const uint64_t v_desc = umma_smem_desc_sw128(sV + uint32_t(key0) * ROW_BYTES, 1024, 1024);
@@ -202,6 +217,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
           }
           umma_commit(o_full);
+          if (timing) {
+            tm5 = clock64();
+            p.dbg[8] += tm1 - tm0; p.dbg[9] += tm2 - tm1; p.dbg[10] += tm3 - tm2; p.dbg[11] += tm4 - tm3;
+            p.dbg[12] += tm5 - tm4;
+          }
         }
         umma_commit(&kv_empty[buf]);
       }
@@ -212,78 +232,95 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int hf = (warp - 4) >> 2;      // which half of the key columns of a row this warp handles
     const int r = q * 32 + lane;         // row inside the tile
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    const int ngroups = (p.tpad + 31) / 32;  // 32-column groups of S (the last one may hold 16 columns)
+    uint8_t* out_stage = smem + OFF_OST + (warp - 4) * 2048;  // 32 rows x 64 B, source of this warp's bulk stores
     uint32_t tile_iter = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int b = pair / p.H, h = pair - b * p.H;
       for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
         const uint32_t par = tile_iter & 1;
+        const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
+        if (timing) tk0 = clock64();
         mbar_wait(s_full, par);
         tc_fence_after();
-        const bool warp_active = t * QT + q * 32 < p.T - p.n_tail;  // any query row of this warp in the tile
+        if (timing) tk1 = clock64();
+        const bool warp_active = kAllRowsLive || t * QT + q * 32 < T - n_tail;  // any query row of this warp in the tile
         const int tok = t * QT + r;
-        // ---- pass 1: row max (this warp: groups with g % 2 == hf)
-        float m = -INFINITY;
-        if (warp_active) {
-          for (int g = hf; g < ngroups; g += 2) {
-            const int c0 = g * 32;
-            uint32_t v[32];
-            if (p.tpad - c0 >= 32) {
-              tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
-            } else {
-              uint32_t w16[16];
-              tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
+        // Key columns are dealt in 64-column chunks: chunk c of this warp = columns [64c + 32hf, +32) (the last one
+        // may hold 16).  Both passes are software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is
+        // reduced / exponentiated (two register buffers, the chunk loop is unrolled by hand).
+        auto chunk_exists = [&](int c) { return warp_active && c < nchunks && c * 64 + hf * 32 < tpad; };
+        auto issue_ld = [&](int c, uint32_t (&v)[32]) {
+          const int c0 = c * 64 + hf * 32;
+          if (tpad - c0 >= 32) {
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
+          } else {
+            tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
-            }
-            tmem_ld_wait();
-            if (c0 + 32 <= p.T) m = max_group<false>(v, 32, m);
-            else                m = max_group<true>(v, p.T - c0, m);
+            for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
           }
-        }
+        };
+        uint32_t va[32], vb[32];
+        // ---- pass 1: row max
+        float m = -INFINITY;
+        auto max_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+          if (!chunk_exists(c)) return;
+          const bool more = chunk_exists(c + 1);
+          if (more) issue_ld(c + 1, nxt);
+          const int c0 = c * 64 + hf * 32;
+          if (c0 + 32 <= T) m = max_group<false>(cur, 32, m);
+          else                m = max_group<true>(cur, T - c0, m);
+          if (more) tmem_ld_wait();
+        };
+        if (chunk_exists(0)) { issue_ld(0, va); tmem_ld_wait(); }
+        max_step(0, va, vb); max_step(1, vb, va); max_step(2, va, vb); max_step(3, vb, va); max_step(4, va, vb);
+        if (timing) tk2 = clock64();
+        if (chunk_exists(0)) issue_ld(0, va);      // pass 2's first chunk travels during the max exchange
         xch_max[hf * 128 + r] = m;
         named_bar_sync(1 + q, 64);
         m = fmaxf(xch_max[r], xch_max[128 + r]);
         const float msl = m * p.sl2;
-        // ---- pass 2: exponentials, row sum, bf16 P into TMEM (chunk c: this warp owns keys [64c + 32hf, +32))
+        if (chunk_exists(0)) tmem_ld_wait();
+        if (timing) tk3 = clock64();
+        // ---- pass 2: exponentials, row sum, bf16 P into TMEM
         float l = 0.f;
-        for (int c = 0; c < p.nchunks; ++c) {
-          const int c0 = c * 64 + hf * 32;
-          if (warp_active && c0 < p.tpad) {
-            const int width = p.tpad - c0 >= 32 ? 32 : 16;
-            uint32_t v[32], pk[16];
-            if (width == 32) {
-              tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
-            } else {
-              uint32_t w16[16];
-              tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, w16);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) { v[j] = w16[j]; v[16 + j] = 0xff800000u; }
-            }
-            tmem_ld_wait();
-            if (c0 + 32 <= p.T) l += exp_group<false>(v, p.sl2, msl, 32, pk);
-            else                l += exp_group<true>(v, p.sl2, msl, p.T - c0, pk);
-            if (width == 32) {
+        auto exp_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+          if (c >= nchunks) return;
+          const bool have = chunk_exists(c), more = chunk_exists(c + 1);
+          if (more) issue_ld(c + 1, nxt);
+          if (have) {
+            const int c0 = c * 64 + hf * 32;
+            uint32_t pk[16];
+            if (c0 + 32 <= T) l += exp_group<false>(cur, p.sl2, msl, 32, pk);
+            else                l += exp_group<true>(cur, p.sl2, msl, T - c0, pk);
+            if (tpad - c0 >= 32) {
               tmem_st_32x32b_x16(tmem_base + lane_addr + P_COL + (c0 >> 1), pk);
             } else {
-              uint32_t pk8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
-              tmem_st_32x32b_x8(tmem_base + lane_addr + P_COL + (c0 >> 1), pk8);
+              tmem_st_32x32b_x8(tmem_base + lane_addr + P_COL + (c0 >> 1), *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
             }
-            tmem_st_wait();
           }
+          if (more) tmem_ld_wait();
+          if (have) tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (c == p.nchunks - 1 && lane == 0) mbar_arrive(s_empty);  // all S reads of this warp are done
+          if (c == nchunks - 1 && lane == 0) mbar_arrive(s_empty);  // all S reads of this warp are done
           if (lane == 0) mbar_arrive(&p_full[c]);
-        }
+        };
+        exp_step(0, va, vb); exp_step(1, vb, va); exp_step(2, va, vb); exp_step(3, vb, va); exp_step(4, va, vb);
+        if (timing) tk4 = clock64();
         xch_sum[hf * 128 + r] = l;
         named_bar_sync(1 + q, 64);
         l = xch_sum[r] + xch_sum[128 + r];
+        if (timing) tk5 = clock64();
         // ---- epilogue: this warp normalises 32 of the 64 output columns
+        const bool full_rows = kAllRowsLive || t * QT + q * 32 + 32 <= T - n_tail;   // all 32 rows of this warp are queries
+        if (full_rows) {
+          if (lane == 0) tma_store_wait_read();   // the previous tile's bulk store has finished reading the staging tile
+          __syncwarp();
+        }
         mbar_wait(o_full, par);
         tc_fence_after();
+        if (timing) tk6 = clock64();
         uint32_t o[32];
         if (warp_active) {
           tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, o);
@@ -292,22 +329,44 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);
-        if (warp_active && tok < p.T - p.n_tail) {
+        if (warp_active && (full_rows || tok < T - n_tail)) {
           const float inv = 1.0f / l;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * p.T + tok) * (p.H * HD) + h * HD + hf * 32);
+          uint4 w[4];
 #pragma unroll
           for (int jv = 0; jv < 4; ++jv) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[jv * 8 + 0]) * inv, __uint_as_float(o[jv * 8 + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[jv * 8 + 2]) * inv, __uint_as_float(o[jv * 8 + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[jv * 8 + 4]) * inv, __uint_as_float(o[jv * 8 + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[jv * 8 + 6]) * inv, __uint_as_float(o[jv * 8 + 7]) * inv);
-            dst[jv] = w;
+            w[jv].x = pack_bf16x2(__uint_as_float(o[jv * 8 + 0]) * inv, __uint_as_float(o[jv * 8 + 1]) * inv);
+            w[jv].y = pack_bf16x2(__uint_as_float(o[jv * 8 + 2]) * inv, __uint_as_float(o[jv * 8 + 3]) * inv);
+            w[jv].z = pack_bf16x2(__uint_as_float(o[jv * 8 + 4]) * inv, __uint_as_float(o[jv * 8 + 5]) * inv);
+            w[jv].w = pack_bf16x2(__uint_as_float(o[jv * 8 + 6]) * inv, __uint_as_float(o[jv * 8 + 7]) * inv);
           }
+          if (full_rows) {
+            // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
+#pragma unroll
+            for (int jv = 0; jv < 4; ++jv)
+              *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((jv ^ ((lane >> 1) & 3)) << 4)) = w[jv];
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * T + tok) * (p.H * HD) + h * HD + hf * 32);
+#pragma unroll
+            for (int jv = 0; jv < 4; ++jv) dst[jv] = w[jv];
+          }
+        }
+        if (full_rows) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, out_stage, h * HD + hf * 32, b * T + t * QT + q * 32);  // 32 rows x 32 columns
+            tma_store_commit();
+          }
+        }
+        if (timing) {
+          const long long tk7 = clock64();
+          p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
+          p.dbg[4] += tk5 - tk4; p.dbg[5] += tk6 - tk5; p.dbg[6] += tk7 - tk6; p.dbg[7] += 1;
         }
       }
     }
-  } else if (warp >= 4 + NUM_SOFTMAX_WARPS && p.n_tail > 0) {
+    if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the bulk stores reading it
+  } else if (warp >= 4 + NUM_SOFTMAX_WARPS && n_tail > 0) {
     // ---------------------------------------------------------------------------- tail queries (<= 8 rows)
     // Warp-level mma.sync.m16n8k16 on the K/V tiles already in shared memory (ldmatrix understands the TMA 128B
     // swizzle: every 8x8 sub-matrix row is one 16-byte chunk).  Keys are dealt to the four warps in blocks of 16;
@@ -315,12 +374,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // leaves registers.  Only rows 0..7 of the 16-row fragments carry queries (rows 8..15 are ignored).
     const int tw = warp - 4 - NUM_SOFTMAX_WARPS;   // 0..3
     const int tt = tw * 32 + lane;                 // 0..127
-    const int nt = p.n_tail;
+    const int nt = n_tail;
     const int g = lane >> 2, tq = lane & 3;        // fragment row group / thread-in-group
     float* to = reinterpret_cast<float*>(smem + OFF_TO);       // [4 warps][8 rows][64]
     float* tredm = reinterpret_cast<float*>(smem + OFF_TRED);  // [4][8]
     float* treds = tredm + NUM_TAIL_WARPS * TAIL_MAX;          // [4][8]
-    const int nblk16 = p.tpad / 16;                // 16-key blocks, dealt round-robin to the warps
+    const int nblk16 = tpad / 16;                // 16-key blocks, dealt round-robin to the warps
     int it = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
       const int b = pair / p.H, h = pair - b * p.H;
@@ -330,11 +389,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t sTQ = smem_u32(smem + OFF_TQ + buf * TAIL_BOX * ROW_BYTES);
       mbar_wait(&kv_full[buf], (it >> 1) & 1);
       mbar_wait(&tq_full[buf], (it >> 1) & 1);
-      if (p.debug_skip_tail) {  // perf experiment: handshakes only
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&kv_empty[buf]); mbar_arrive(&tq_empty[buf]); }
-        continue;
-      }
       // ---- A fragments of the tail queries: 16 rows x 64 dims = 4 k-steps x {a0..a3}
       uint32_t qa[4][4];
 #pragma unroll
@@ -369,8 +423,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int tile = 0; tile < 2; ++tile) {
             const int k0 = blk * 16 + tile * 8 + 2 * tq;  // keys of c0, c1
-            if (k0 < p.T) mrow = fmaxf(mrow, sacc[bi][tile][0]);
-            if (k0 + 1 < p.T) mrow = fmaxf(mrow, sacc[bi][tile][1]);
+            if (k0 < T) mrow = fmaxf(mrow, sacc[bi][tile][0]);
+            if (k0 + 1 < T) mrow = fmaxf(mrow, sacc[bi][tile][1]);
           }
         }
       }
@@ -395,8 +449,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int tile = 0; tile < 2; ++tile) {
             const int k0 = blk * 16 + tile * 8 + 2 * tq;
-            const float e0 = k0 < p.T ? ex2(fmaf(sacc[bi][tile][0], p.sl2, -msl)) : 0.f;
-            const float e1 = k0 + 1 < p.T ? ex2(fmaf(sacc[bi][tile][1], p.sl2, -msl)) : 0.f;
+            const float e0 = k0 < T ? ex2(fmaf(sacc[bi][tile][0], p.sl2, -msl)) : 0.f;
+            const float e1 = k0 + 1 < T ? ex2(fmaf(sacc[bi][tile][1], p.sl2, -msl)) : 0.f;
             lsum += e0 + e1;
             pa[2 * tile] = pack_bf16x2(e0, e1);   // rows g     (a0 / a2)
             pa[2 * tile + 1] = 0u;                // rows g + 8 (a1 / a3): unused query rows
@@ -433,8 +487,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const float l = (treds[j] + treds[TAIL_MAX + j]) + (treds[2 * TAIL_MAX + j] + treds[3 * TAIL_MAX + j]);
         const float inv = 1.0f / l;
-        const int tok = p.T - nt + j;
-        *reinterpret_cast<uint32_t*>(p.out + (size_t(b) * p.T + tok) * (p.H * HD) + h * HD + 2 * dp) =
+        const int tok = T - nt + j;
+        *reinterpret_cast<uint32_t*>(p.out + (size_t(b) * T + tok) * (p.H * HD) + h * HD + 2 * dp) =
             pack_bf16x2(acc.x * inv, acc.y * inv);
       }
       named_bar_sync(6, NUM_TAIL_WARPS * 32);  // smem scratch is reused by the next pair
@@ -456,28 +510,35 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   const int n_tail = (rem > 0 && rem <= TAIL_MAX) ? rem : 0;
   const int n_normal = T / QT + ((rem > TAIL_MAX) ? 1 : 0);
   const int C = 3 * H * HD;
-  CUtensorMap tmQ, tmQt, tmKV;
+  CUtensorMap tmQ, tmQt, tmKV, tmOut;
   const uint64_t rows = uint64_t(B) * T;
   if (int rc = make_tmap_2d_bf16(&tmQ, qkv, rows, uint64_t(C), uint64_t(C), QT, HD)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmQt, qkv, rows, uint64_t(C), uint64_t(C), TAIL_BOX, HD)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmKV, qkv, rows, uint64_t(C), uint64_t(C), uint32_t(tpad / 2), HD)) return rc;
+  if (int rc = make_tmap_2d_bf16_sw64(&tmOut, out, rows, uint64_t(H) * HD, uint64_t(H) * HD, 32)) return rc;
   Params p;
   p.out = out; p.B = B; p.T = T; p.H = H;
   p.tpad = tpad; p.n_normal = n_normal; p.n_tail = n_tail;
-  if (getenv("FP_ATTN_NOTAIL")) p.n_tail = 0;
-  p.debug_skip_tail = getenv("FP_ATTN_SKIPTAIL") ? 1 : 0;
-  p.dbg = nullptr;  // perf experiment: skips the tail rows (wrong results)
+  // perf experiment: FP_ATTN_DBG = device address of 16 int64 phase counters (softmax warp 4 / MMA warp of CTA 0)
+  p.dbg = getenv("FP_ATTN_DBG") ? reinterpret_cast<long long*>(strtoull(getenv("FP_ATTN_DBG"), nullptr, 0)) : nullptr;
   p.nchunks = (tpad + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS;
   p.sl2 = scale * 1.4426950408889634f;
   static bool attr_done = false;
   if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FP_CUDA(cudaFuncSetAttribute(attention_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FP_CUDA(cudaFuncSetAttribute(attention_kernel<false, 261>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FP_CUDA(cudaFuncSetAttribute(attention_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FP_CUDA(cudaFuncSetAttribute(attention_kernel<true, 261>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   const int npairs = B * H;
   const int grid = npairs < sm_count() ? npairs : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
-  attention_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, qkv, p);
+  const bool special = T == 261 && !getenv("FP_ATTN_GENERIC");  // 224^2 crops: (224/14)^2 + 5 tokens
+  if (p.dbg && special) attention_kernel<true, 261><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
+  else if (p.dbg)    attention_kernel<true, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
+  else if (special)  attention_kernel<false, 261><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
+  else               attention_kernel<false, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
   FP_CUDA(cudaGetLastError());
   return 0;
 }
