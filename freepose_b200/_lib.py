@@ -64,6 +64,12 @@ SIGNATURES = {
     "fp_score_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "fp_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "fp_ffa_pool": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "fp_normalize_rows": (_i, [_vp, _i, C.c_int64, _i, _vp, _vp]),
+    "fp_retrieval_scan": (_i, [_vp, _vp, C.c_int64, _i, _i, _vp, _vp]),
+    "fp_topk_rows": (_i, [_vp, _i, C.c_int64, _i, _vp, _vp, _vp]),
+    "fp_retrieval_fine": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "fp_softvote_add": (_i, [_vp, _vp, _vp, _i, _i, C.c_int64, _vp]),
+    "fp_softvote_mean": (_i, [_vp, _vp, C.c_int64, _i, _vp]),
     "fp_raster_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
     "fp_rasterize": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp]),
     "fp_mask_bbox": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -89,6 +89,34 @@ FP_API int fp_ffa_pool(const void* feats, const uint8_t* masks, int V, int res, 
   return fp::ffa_pool(B16(feats), masks, V, res, res / 14, D, out, valid, S(stream));
 }
 
+FP_API int fp_normalize_rows(const void* src, int src_is_f32, int64_t rows, int D, void* dst_bf16, void* stream) {
+  return fp::normalize_rows(src, src_is_f32, rows, D, B16(dst_bf16), S(stream));
+}
+
+FP_API int fp_retrieval_scan(const void* db, const void* queries, int64_t M, int D, int Q, float* scores,
+                             void* stream) {
+  return fp::retrieval_scan(B16(db), B16(queries), M, D, Q, scores, S(stream));
+}
+
+FP_API int fp_topk_rows(const float* scores, int Q, int64_t M, int k, int32_t* idx, float* val, void* stream) {
+  return fp::topk_rows(scores, Q, M, k, idx, val, S(stream));
+}
+
+FP_API int fp_retrieval_fine(const void* views, const int64_t* view_start, const int32_t* view_count, int max_views,
+                             const int32_t* cand, const void* queries, int Q, int C, int D, int k, float* out,
+                             void* stream) {
+  return fp::retrieval_fine(B16(views), reinterpret_cast<const long long*>(view_start), view_count, max_views, cand,
+                            B16(queries), Q, C, D, k, out, S(stream));
+}
+
+FP_API int fp_softvote_add(float* acc, const int32_t* idx, const float* val, int P, int C, int64_t M, void* stream) {
+  return fp::softvote_add(acc, idx, val, P, C, M, S(stream));
+}
+
+FP_API int fp_softvote_mean(const float* acc, float* out, int64_t n, int frames, void* stream) {
+  return fp::softvote_mean(acc, out, n, frames, S(stream));
+}
+
 FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
   return fp::raster_workspace_bytes(B, V, res, msaa, bytes);
 }

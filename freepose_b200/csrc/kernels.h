@@ -74,6 +74,20 @@ int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val,
 int ffa_pool(const bf16* feats, const uint8_t* masks, int V, int res, int g, int D, float* out,
              int* valid, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------- retrieval (retrieval.cu)
+// F.normalize(x.to(bf16), dim=-1) row-wise; src fp32 or bf16 [M, D] -> dst bf16 [M, D].
+int normalize_rows(const void* src, int src_is_f32, long long M, int D, bf16* dst, cudaStream_t stream);
+// scores[q, m] = bf16(db[m] . queries[q]) as fp32; db [M, D], queries [Q, D], both bf16 and already normalised.
+int retrieval_scan(const bf16* db, const bf16* queries, long long M, int D, int Q, float* scores, cudaStream_t stream);
+// per row of scores [Q, M]: top-k (k <= 1024) descending, NaN first, ties -> lowest index; idx/val [Q, k].
+int topk_rows(const float* scores, int Q, long long M, int k, int* idx, float* val, cudaStream_t stream);
+// out[q, c] = float32 mean of the top-k per-view scores of candidate mesh cand[q, c] (views of mesh m are rows
+// view_start[m] .. +view_count[m] of `views`, normalised bf16); cand < 0 -> -inf.
+int retrieval_fine(const bf16* views, const long long* view_start, const int* view_count, int max_views,
+                   const int* cand, const bf16* queries, int Q, int C, int D, int k, float* out, cudaStream_t stream);
+int softvote_add(float* acc, const int* idx, const float* val, int P, int C, long long M, cudaStream_t stream);
+int softvote_mean(const float* acc, float* out, long long n, int frames, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------- raster
 struct RasterArgs {
   const float* verts;     // [V, 3] fp32 object-space

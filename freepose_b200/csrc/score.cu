@@ -14,42 +14,14 @@
 // HBM-bound: every template token row (2 KB) is read exactly once; one CTA per hypothesis.
 #include "common.cuh"
 #include "kernels.h"
+#include "rowops.cuh"
 
 namespace fp {
 
 namespace {
 
 constexpr int SC_WARPS = 8;
-constexpr int MAX_CHUNKS = 4;  // D <= 1024
-
-__device__ __forceinline__ void load_row(const bf16* row, int lane, int chunks, uint4 (&u)[MAX_CHUNKS]) {
-  const uint4* p = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < chunks) u[c] = p[c * 32 + lane];
-}
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
-  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
-}
-
-// bf16(sqrt(sum x^2)) clamped below by bf16(eps), as float
-__device__ __forceinline__ float row_norm(const uint4 (&u)[MAX_CHUNKS], int chunks) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < MAX_CHUNKS; ++c)
-    if (c < chunks) {
-      float f[8];
-      unpack8(u[c], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, __fmul_rn(f[j], f[j]));
-    }
-  acc = warp_sum(acc);
-  const float nrm = bf16_round(__fsqrt_rn(acc));
-  const float eps = bf16_round(1e-12f);
-  return fmaxf(nrm, eps);
-}
+using namespace rowops;
 
 // qn = normalised (or verbatim) query tokens, one warp per row
 __global__ void __launch_bounds__(SC_WARPS * 32)

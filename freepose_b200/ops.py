@@ -126,6 +126,65 @@ def ffa_pool(feats: torch.Tensor, masks: torch.Tensor):
     return out, valid
 
 
+# ------------------------------------------------------------------------------------------- retrieval
+def normalize_rows(x: torch.Tensor, out: torch.Tensor | None = None):
+    """F.normalize(x.to(bfloat16), dim=-1) for x (rows, D) fp32 or bf16 on the device -> (rows, D) bf16."""
+    assert x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    check(load().fp_normalize_rows(ptr(x), int(x.dtype == torch.float32), rows, D, ptr(out), stream_ptr()),
+          "fp_normalize_rows")
+    return out
+
+
+def retrieval_scan(db: torch.Tensor, queries: torch.Tensor):
+    """db (M,D), queries (Q,D): normalised bf16 -> (Q,M) fp32 scores (bf16-valued, like ``(db @ q).float()``)."""
+    assert db.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and db.shape[1] == queries.shape[1]
+    M, D = db.shape
+    Q = queries.shape[0]
+    scores = torch.empty(Q, M, dtype=torch.float32, device=db.device)
+    check(load().fp_retrieval_scan(ptr(db), ptr(queries), M, D, Q, ptr(scores), stream_ptr()), "fp_retrieval_scan")
+    return scores
+
+
+def topk_rows(scores: torch.Tensor, k: int):
+    """torch.topk(scores, k, dim=1) with a defined tie order (lowest index): (Q,M) fp32 -> idx (Q,k) int32, val (Q,k)."""
+    assert scores.dim() == 2 and scores.dtype == torch.float32
+    Q, M = scores.shape
+    idx = torch.empty(Q, k, dtype=torch.int32, device=scores.device)
+    val = torch.empty(Q, k, dtype=torch.float32, device=scores.device)
+    check(load().fp_topk_rows(ptr(scores), Q, M, k, ptr(idx), ptr(val), stream_ptr()), "fp_topk_rows")
+    return idx, val
+
+
+def retrieval_fine(views: torch.Tensor, view_start: torch.Tensor, view_count: torch.Tensor, max_views: int,
+                   cand: torch.Tensor, queries: torch.Tensor, k: int):
+    """Per candidate mesh: float32 mean of the top-k per-view scores.  views (N,D) normalised bf16, view_start (M,)
+    int64 / view_count (M,) int32 rows of each mesh, cand (Q,C) int32, queries (Q,D) bf16 -> (Q,C) fp32."""
+    assert views.dtype == torch.bfloat16 and view_start.dtype == torch.int64 and view_count.dtype == torch.int32
+    assert cand.dtype == torch.int32 and queries.dtype == torch.bfloat16
+    Q, C = cand.shape
+    out = torch.empty(Q, C, dtype=torch.float32, device=views.device)
+    check(load().fp_retrieval_fine(ptr(views), ptr(view_start), ptr(view_count), int(max_views), ptr(cand),
+                                   ptr(queries), Q, C, views.shape[1], k, ptr(out), stream_ptr()), "fp_retrieval_fine")
+    return out
+
+
+def softvote_add(acc: torch.Tensor, idx: torch.Tensor, val: torch.Tensor):
+    """acc (P,M) fp32 += one frame's sparse scores: idx (P,C) int32 (unique per row, <0 skipped), val (P,C) fp32."""
+    assert acc.dtype == torch.float32 and idx.dtype == torch.int32 and val.dtype == torch.float32
+    P, C = idx.shape
+    check(load().fp_softvote_add(ptr(acc), ptr(idx), ptr(val), P, C, acc.shape[1], stream_ptr()), "fp_softvote_add")
+    return acc
+
+
+def softvote_mean(acc: torch.Tensor, frames: int):
+    out = torch.empty_like(acc)
+    check(load().fp_softvote_mean(ptr(acc), ptr(out), acc.numel(), frames, stream_ptr()), "fp_softvote_mean")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- raster
 @functools.lru_cache(maxsize=None)
 def _gamma_lut_host() -> np.ndarray:

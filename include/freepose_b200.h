@@ -132,6 +132,30 @@ FP_API int fp_ffa_pool(const void* feats, const uint8_t* masks, int V, int res, 
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Mesh retrieval
+ * replaces: scripts/extract_proposals_ground.py:39-41 (database normalisation), :136-160 (coarse scan, topk(100),
+ *           per-view fine re-rank) and scripts/extract_proposals_ground_video.py:148-190 (same + soft vote over frames)
+ * All feature rows have D = 256, 512, 768 or 1024 elements.  Top-k order: NaN first, descending, ties -> lowest index.
+ * ------------------------------------------------------------------------------------------------ */
+/* F.normalize(x.to(bfloat16), dim=-1): src (rows,D) fp32 or bf16 -> dst (rows,D) bf16 */
+FP_API int fp_normalize_rows(const void* src, int src_is_f32, int64_t rows, int D, void* dst_bf16, void* stream);
+/* scores[q,m] = float(bf16(db[m] . queries[q])): db (M,D) and queries (Q,D) normalised bf16 -> scores (Q,M) fp32.
+ * The database is read once for up to 32 queries. */
+FP_API int fp_retrieval_scan(const void* db, const void* queries, int64_t M, int D, int Q, float* scores,
+                             void* stream);
+/* torch.topk(scores[q], k) for every row: scores (Q,M) fp32 -> idx (Q,k) int32, val (Q,k) fp32; k <= 1024 */
+FP_API int fp_topk_rows(const float* scores, int Q, int64_t M, int k, int32_t* idx, float* val, void* stream);
+/* fine re-rank: views = device-resident per-view features of the meshes, normalised bf16, mesh m owning rows
+ * view_start[m] .. view_start[m]+view_count[m]; cand (Q,C) int32 mesh indices (<0: skipped, -inf).  out[q,c] = float32
+ * numpy-order mean of topk(views(cand[q,c]) . queries[q], k).  k <= 128, views per mesh <= 4096. */
+FP_API int fp_retrieval_fine(const void* views, const int64_t* view_start, const int32_t* view_count, int max_views,
+                             const int32_t* cand, const void* queries, int Q, int C, int D, int k, float* out,
+                             void* stream);
+/* video soft vote: acc (P,M) fp32 += scatter of one frame's (idx, val) (P,C); then mean over `frames` */
+FP_API int fp_softvote_add(float* acc, const int32_t* idx, const float* val, int P, int C, int64_t M, void* stream);
+FP_API int fp_softvote_mean(const float* acc, float* out, int64_t n, int frames, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Rasteriser
  * replaces: src/pipeline/retrieval/renderer.py:43-95 (MeshRenderer.render / render_from_poses: one pyrender
  *           GL draw + glReadPixels per pose)

@@ -135,6 +135,34 @@ def golden_score():
                         argmax=torch.argmax(scores).numpy(), maxval=torch.max(scores).float().numpy())
 
 
+def golden_retrieval():
+    """The reference's retrieval lines (extract_proposals_ground.py:39-41,136-160, ..._video.py:148-190) restated in
+    oracle/retrieval.py reference_* and run on CPU bf16; inputs are regenerated from the seed at test time."""
+    import torch.nn.functional as F
+    from oracle import retrieval as R
+    case = R.synthetic_case(0)
+    dbn = R.reference_database(case["db"])
+    feats = F.normalize(torch.from_numpy(case["queries"]).to(torch.bfloat16), dim=-1)
+    store = {"db_sha": np.frombuffer(bytes.fromhex(sha(case["db"])), dtype=np.uint8),
+             "db_norm": dbn[:16].view(torch.int16).numpy()}
+    for topk in (0, 3, 10):
+        best, score, cand, dense = [], [], [], []
+        for f in feats:
+            m, sc, I, s = R.reference_retrieve(dbn, case["fine"], f, topk)
+            best.append(m); score.append(sc); cand.append(I); dense.append(s[torch.from_numpy(I)].numpy())
+        store[f"best_{topk}"] = np.array(best)
+        store[f"score_{topk}"] = np.array(score, dtype=np.float64)
+        store[f"cand_{topk}"] = np.stack(cand)
+        store[f"cand_scores_{topk}"] = np.stack(dense)
+    per_frame = []
+    for fr in case["video"]:
+        ff = F.normalize(torch.from_numpy(fr).to(torch.bfloat16), dim=-1)
+        per_frame.append(torch.stack([R.reference_retrieve(dbn, case["fine"], f, 3)[3] for f in ff]))
+    I, sc = R.reference_softvote(per_frame)
+    store["vote_best"], store["vote_score"] = I, sc
+    np.savez_compressed(OUT / "retrieval.npz", **store)
+
+
 if __name__ == "__main__":
     assert refimport.available(), "/root/reference is required to mint fixtures"
     torch.set_num_threads(1)
@@ -143,5 +171,6 @@ if __name__ == "__main__":
     golden_crop()
     golden_dino_forward()
     golden_score()
+    golden_retrieval()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -390,3 +390,105 @@ def test_depth_extents_vs_reference_geometry(ops, golden):
     e = ops.depth_extents(d, np.array([[320.0, 0, 112], [0, 320.0, 112], [0, 0, 1]]),
                           view_idx=torch.tensor([1, 0], device=dev)).cpu().numpy()
     assert e[0, 7] == 200 and e[1, 7] == 0
+
+
+# ------------------------------------------------------------------------------------------- mesh retrieval
+def test_normalize_rows_and_scan_bit_exact(ops):
+    from oracle import retrieval as R
+    rng = np.random.default_rng(5)
+    for M, D, Q in ((1, 1024, 1), (37, 1024, 3), (2500, 1024, 33), (300, 768, 2), (64, 256, 5)):
+        db = rng.standard_normal((M, D)).astype(np.float32) * rng.uniform(0.1, 30, size=(M, 1)).astype(np.float32)
+        if M > 2:
+            db[1] = 0                                                   # zero row: clamped by eps, stays 0
+        qs = rng.standard_normal((Q, D)).astype(np.float32)
+        dbn, qn = R.engine_normalize(db), R.engine_normalize(qs)
+        got_db = ops.normalize_rows(torch.from_numpy(db).to(dev))
+        assert torch.equal(got_db.float().cpu(), torch.from_numpy(dbn))
+        # bf16 input path == fp32 input path after the cast
+        assert torch.equal(ops.normalize_rows(torch.from_numpy(db).to(bf).to(dev)), got_db)
+        got_q = ops.normalize_rows(torch.from_numpy(qs).to(dev))
+        scores = ops.retrieval_scan(got_db, got_q).cpu().numpy()
+        assert np.array_equal(scores, R.engine_scan(dbn, qn))
+
+
+@pytest.mark.parametrize("M,k", [(1, 1), (100, 100), (1000, 3), (5000, 100), (46037, 100), (46037, 1024), (70000, 517)])
+def test_topk_rows_bit_exact_with_ties_and_specials(ops, M, k):
+    from oracle.retrieval import engine_topk
+    rng = np.random.default_rng(M + k)
+    s = torch.from_numpy(rng.standard_normal((3, M)).astype(np.float32)).to(bf).float().numpy()  # bf16-valued: many ties
+    s[1] = np.round(s[1] * 4) / 4                                                                # massive ties
+    if M >= 1000:
+        s[2, 5], s[2, 17], s[2, 400], s[2, 401], s[2, 402] = np.nan, np.inf, -np.inf, 0.0, -0.0
+        s[2, 900] = np.nan
+    idx, val = ops.topk_rows(torch.from_numpy(s).to(dev), k)
+    ridx, rval = engine_topk(s, k)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(val.cpu().numpy(), rval, equal_nan=True)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ops.topk_rows(torch.zeros(1, 4, device=dev), 5)
+
+
+def test_retrieval_database_vs_oracle_and_reference_fixture(ops, golden):
+    from freepose_b200.pipeline.retrieval.database import RetrievalDatabase, SoftVote
+    from oracle import retrieval as R
+    g = golden["retrieval"]
+    case = R.synthetic_case(0)
+    dbn = R.engine_normalize(case["db"])
+    qn = R.engine_normalize(case["queries"])
+    loads = []
+
+    def loader(m):
+        loads.append(m)
+        return case["fine"][m]
+
+    db = RetrievalDatabase(case["db"], case["ids"], fine_loader=loader, pool_views=100 * 8 * 40)
+    feats = db.normalize(torch.from_numpy(case["queries"]))
+    assert torch.equal(feats.float().cpu(), torch.from_numpy(qn))
+    for topk in (0, 3, 10):
+        meshes, scores, cand, cs = db.retrieve(feats, topk=topk, return_sparse=True)
+        best, score, ecand, ecs = R.engine_retrieve(dbn, case["fine"], qn, topk)
+        assert np.array_equal(cand.cpu().numpy(), ecand)                       # candidate indices: bit-exact
+        assert np.array_equal(cs.cpu().numpy(), ecs)                           # coarse / fine scores: bit-exact
+        assert meshes == [case["ids"][m] for m in best] and np.array_equal(np.float32(scores), score)
+        assert meshes == [case["ids"][m] for m in g[f"best_{topk}"]]           # = the reference lines' retrieval
+        assert np.array_equal(np.float64(scores), g[f"score_{topk}"])
+    assert len(loads) == len(set(loads))                                       # every mesh file read at most once
+    # preloaded store gives the same answer
+    db2 = RetrievalDatabase(case["db"], case["ids"], fine_features=case["fine"])
+    assert db2.retrieve(feats, topk=3) == db.retrieve(feats, topk=3)
+    with pytest.raises(RuntimeError, match="out of range"):
+        db2.retrieve(feats, topk=60)                                           # more than a mesh has views (torch raises)
+    # video soft vote
+    vote, per_frame = SoftVote(db, 3), []
+    for fr in case["video"]:
+        f = db.normalize(torch.from_numpy(fr))
+        _, _, cand, cs = db.retrieve(f, topk=3, return_sparse=True)
+        vote.add_frame(cand, cs)
+        per_frame.append((cand.cpu().numpy(), cs.cpu().numpy()))
+    vm, vs = vote.result()
+    ebest, escore, emean = R.engine_softvote_dense(per_frame, db.M)
+    assert vm == [case["ids"][m] for m in ebest] and np.array_equal(np.float32(vs), escore)
+    assert vm == [case["ids"][m] for m in g["vote_best"]]
+    np.testing.assert_allclose(np.float32(vs), g["vote_score"], rtol=1e-6)
+
+
+def test_retrieval_full_size_properties(ops):
+    """46 037 x 1024 (the reference's table size): planted rows must come out on top, scan is linear in the query count."""
+    from freepose_b200.pipeline.retrieval.database import RetrievalDatabase
+    g = torch.Generator(device=dev).manual_seed(0)
+    M, D, Q = 46037, 1024, 12
+    table = torch.randn(M, D, device=dev, generator=g)
+    planted = torch.randint(0, M, (Q,), device=dev, generator=g)
+    queries = table[planted] + 0.3 * torch.randn(Q, D, device=dev, generator=g)
+    db = RetrievalDatabase(table, [str(i) for i in range(M)])
+    feats = db.normalize(queries)
+    val, idx = db.coarse(feats)
+    assert torch.equal(idx[:, 0].long(), planted)
+    assert torch.all(val[:, :-1] >= val[:, 1:])                                 # sorted
+    full = db.scores(feats)
+    assert torch.equal(full[3:4], db.scores(feats[3:4]))                        # batch invariance
+    assert torch.equal(full.gather(1, idx.long()), val)
+    kth = val[:, -1:]
+    assert torch.all((full > kth).sum(1) <= 99) and torch.all((full >= kth).sum(1) >= 100)
+    meshes, scores = db.retrieve(feats)
+    assert meshes == [str(int(i)) for i in planted]

@@ -130,3 +130,64 @@ def test_ffa_oracles_agree():
     # sequential vs ATen summation order: identical up to rare single bf16-ulp flips
     d = np.abs(ref[:4] - eng[:4])
     assert (d > 0).mean() < 0.01 and np.all(d <= np.abs(ref[:4]) * 2 ** -7 + 1e-30)
+
+
+# ------------------------------------------------------------------------------------------- mesh retrieval
+def _tie_consistent(cand, vals, ref_cand, ref_vals):
+    """Two top-k selections of the same score vector may differ only inside the tie at the cut-off value."""
+    assert np.array_equal(np.sort(vals), np.sort(ref_vals))             # same multiset of values
+    cut = vals.min()
+    ours, theirs = dict(zip(cand.tolist(), vals.tolist())), dict(zip(ref_cand.tolist(), ref_vals.tolist()))
+    for m in set(ours) ^ set(theirs):
+        assert ours.get(m, theirs.get(m)) == cut
+    return set(ours) & set(theirs)
+
+
+def test_retrieval_oracles_match_reference_lines(golden):
+    from oracle import retrieval as R
+    g = golden["retrieval"]
+    case = R.synthetic_case(0)
+    assert sha(case["db"]) == bytes(g["db_sha"]).hex()                  # the seeded inputs are the minted ones
+    dbn = R.engine_normalize(case["db"])
+    ref16 = torch.from_numpy(g["db_norm"]).view(torch.bfloat16).float().numpy()
+    assert np.array_equal(dbn[:16], ref16)
+    qn = R.engine_normalize(case["queries"])
+    for topk in (0, 3, 10):
+        best, score, cand, cs = R.engine_retrieve(dbn, case["fine"], qn, topk)
+        assert np.array_equal(best, g[f"best_{topk}"])                  # retrieved mesh: bit-exact
+        assert np.array_equal(score.astype(np.float64), g[f"score_{topk}"])
+        for q in range(cand.shape[0]):
+            if topk == 0:
+                _tie_consistent(cand[q], cs[q], g["cand_0"][q], g["cand_scores_0"][q])
+            else:  # candidates present in both selections carry identical fine scores
+                coarse = R.engine_topk(R.engine_scan(dbn, qn[q:q + 1])[0], 100)[1]
+                ours = dict(zip(cand[q].tolist(), cs[q].tolist()))
+                theirs = dict(zip(g[f"cand_{topk}"][q].tolist(), g[f"cand_scores_{topk}"][q].tolist()))
+                shared = set(ours) & set(theirs)
+                assert len(shared) >= 90 and all(ours[m] == theirs[m] for m in shared), coarse[-1]
+    # duplicated rows 3 / 7: identical scores, the lower index wins
+    assert best[1] == 3 and 7 in cand[1]
+
+
+def test_retrieval_softvote_matches_reference_lines(golden):
+    from oracle import retrieval as R
+    g = golden["retrieval"]
+    case = R.synthetic_case(0)
+    dbn = R.engine_normalize(case["db"])
+    per_frame = []
+    for fr in case["video"]:
+        _, _, cand, cs = R.engine_retrieve(dbn, case["fine"], R.engine_normalize(fr), 3)
+        per_frame.append((cand, cs))
+    best, score, _ = R.engine_softvote_dense(per_frame, dbn.shape[0])
+    assert np.array_equal(best, g["vote_best"])
+    # torch.mean sums the frames in its own (cascade) order: values agree to fp32 round-off, the argmax exactly
+    np.testing.assert_allclose(score, g["vote_score"], rtol=1e-6)
+
+
+def test_numpy_order_mean_is_numpy_mean():
+    from oracle.retrieval import numpy_order_mean
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 7, 8, 9, 15, 16, 17, 31, 64, 100, 128):
+        for _ in range(10):
+            v = rng.standard_normal(n).astype(np.float32)
+            assert numpy_order_mean(v) == v.mean()
