@@ -3,13 +3,17 @@
 // single pass (no online rescale).
 //
 //   warp 0        TMA loader   K,V (double buffered across pairs), Q tiles through a 2-slot ring, tail-query rows
-//   warp 1        MMA issuer   S = Q K^T (M128 x N{256,+16} x K64, fp32 accumulators in TMEM)
-//                              O = P V   (P read straight from TMEM -- "TS" form --, V as MN-major smem operand)
+//   warp 1        MMA issuer   S = Q K^T (M128 x N{128, tpad-128} x K64, fp32 accumulators in TMEM), issued in two key
+//                              halves so that the next tile's logits are produced while the softmax warps are still
+//                              exponentiating the current tile (the low half as soon as its columns have been consumed)
+//                              O = P V   (P read straight from TMEM -- "TS" form --, V as MN-major smem operand);
+//                              O is double buffered so a tile's normalisation/store is deferred into the next tile
 //   warp 2        TMEM allocator
 //   warps 4..11   softmax      two warps per TMEM lane quarter split the key columns of every row: row max,
 //                              p = exp2((s - max) * scale*log2e) in fp32, row sum of the unrounded p, P rounded to
-//                              bf16 and stored back into TMEM with tcgen05.st (no shared-memory round trip), then
-//                              O / rowsum -> bf16 -> HBM.
+//                              bf16 and stored with tcgen05.st over the logit columns it was computed from (no extra
+//                              TMEM, no shared-memory round trip); O / rowsum -> bf16 -> HBM of the previous tile
+//                              runs between two exponential chunks of the current one.
 //   warps 12..15  tail queries token counts such as 261 = 2*128 + 5 leave a query tile with a handful of rows (cls +
 //                              registers).  As a tensor-core tile they cost as much as a full one (measured: T=261
 //                              took 1.83x the time of T=256), so remainders of <= 8 rows are computed on the CUDA cores
@@ -40,17 +44,17 @@ constexpr int NUM_SOFTMAX_WARPS = 8;
 constexpr int NUM_TAIL_WARPS = 4;
 constexpr int NUM_THREADS = 128 + (NUM_SOFTMAX_WARPS + NUM_TAIL_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0;      // 272 fp32 columns
-constexpr int P_COL = 272;    // 136 columns of packed bf16x2
-constexpr int O_COL = 408;    // 64 fp32 columns
+constexpr int S_COL = 0;      // 272 fp32 logit columns; bf16x2 P overwrites the first half of every consumed 32-column group
+constexpr int O_COL = 272;    // 2 x 64 fp32 columns (double buffered across tiles)
+constexpr int S_PART = 128;   // S is issued as keys [0,128), [128,256), [256,tpad): a part of the next tile follows the last P.V that reads it
 constexpr int MAX_CHUNKS = 5; // 64-key chunks of P
 constexpr int P_CHUNK_KEYS = 64;
 
 constexpr int OFF_Q = 0;                           // 2 ring slots
 constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;    // 2 buffers
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;        // 2 buffers
-constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2][128] max + [2][128] sum
-constexpr int OFF_TQ = OFF_XCH + 4 * 128 * 4;      // tail Q rows: 2 slots x 16 rows x 128 B (TMA, 128B swizzle)
+constexpr int OFF_XCH = OFF_V + 2 * KV_BYTES;      // float [2 tile parities][2 halves][128] max + the same for sum
+constexpr int OFF_TQ = OFF_XCH + 8 * 128 * 4;      // tail Q rows: 2 slots x 16 rows x 128 B (TMA, 128B swizzle)
 constexpr int OFF_OST = OFF_TQ + 2 * TAIL_BOX * ROW_BYTES;   // output staging: 8 softmax warps x (32 rows x 64 B), 64B swizzle
 constexpr int OFF_TO = OFF_OST + NUM_SOFTMAX_WARPS * 2048;   // float [4 warps][8][64]: partial P.V of the tail rows
 static_assert(OFF_OST % 1024 == 0, "TMA store staging must keep the swizzle alignment");
@@ -73,7 +77,7 @@ using namespace attn;
 
 // T_CONST: token count known at compile time (261 = the 224^2 crops of the headline path: every chunk width, mask and
 // trip count folds to a constant and the straddling-group code is emitted once); 0 = any T <= 272 at run time.
-template <bool TIMING, int T_CONST>
+template <bool TIMING, int T_CONST, unsigned POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQt,
                  const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmOut, const Params p) {
@@ -85,16 +89,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* kv_empty = bars + 2;   // [2]  MMA commit (+ the four tail warps when there are tail rows)
   uint64_t* q_full = bars + 4;     // [2]
   uint64_t* q_empty = bars + 6;    // [2]
-  uint64_t* s_full = bars + 8;
-  uint64_t* s_empty = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint64_t* o_empty = bars + 11;
-  uint64_t* p_full = bars + 12;    // [MAX_CHUNKS]
-  uint64_t* tq_full = bars + 17;   // [2]
-  uint64_t* tq_empty = bars + 19;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
-  float* xch_max = reinterpret_cast<float*>(smem + OFF_XCH);        // [2][128]
-  float* xch_sum = xch_max + 2 * 128;                                // [2][128]
+  uint64_t* s_full = bars + 8;      // [3]  key columns [0,128) / [128,256) / [256,tpad) of S
+  uint64_t* o_full = bars + 11;    // [2]
+  uint64_t* o_empty = bars + 13;   // [2]
+  uint64_t* p_full = bars + 15;    // [MAX_CHUNKS]; all eight arrivals on chunk c also mean "S columns of chunk c are consumed"
+  uint64_t* tq_full = bars + 20;   // [2]
+  uint64_t* tq_empty = bars + 22;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
+  float* xch_max = reinterpret_cast<float*>(smem + OFF_XCH);        // [2 parities][2 halves][128]
+  float* xch_sum = xch_max + 4 * 128;                                // [2 parities][2 halves][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = p.B * p.H;
@@ -120,8 +123,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
       mbar_init(&tq_full[i], 1); mbar_init(&tq_empty[i], NUM_TAIL_WARPS);
     }
-    mbar_init(s_full, 1); mbar_init(s_empty, NUM_SOFTMAX_WARPS);
-    mbar_init(o_full, 1); mbar_init(o_empty, NUM_SOFTMAX_WARPS);
+    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], NUM_SOFTMAX_WARPS); }
     for (int i = 0; i < MAX_CHUNKS; ++i) mbar_init(&p_full[i], NUM_SOFTMAX_WARPS);
     fence_barrier_init();
   }
@@ -164,66 +167,98 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------- MMA issuer
-    if (lane == 0 && tiles_per_pair > 0) {
-      const int n1 = tpad > 256 ? 256 : tpad;
-      const int n2 = tpad - n1;
-      const uint32_t idesc_s1 = umma_idesc_bf16(QT, n1, 0, 0);
-      const uint32_t idesc_s2 = umma_idesc_bf16(QT, n2 > 0 ? n2 : 16, 0, 0);
+    // One thread feeds the tensor pipe, so its scalar instruction stream is on the critical path (measured: with
+    // descriptors rebuilt and run-time loop bounds per MMA the issue rate was ~150 cycles per tcgen05.mma and the pipe
+    // starved).  Everything below is therefore base + compile-time offset: descriptors are built once, chunk / k-step
+    // loops are fully unrolled, tile coordinates advance incrementally (no divisions).
+    if (tiles_per_pair > 0 && elect_one()) {
       const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);  // B (= V) is MN-major
-      uint32_t tile_iter = 0;
-      int it = 0;
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t sK = smem_u32(smem + OFF_K + buf * KV_BYTES);
-        const uint32_t sV = smem_u32(smem + OFF_V + buf * KV_BYTES);
-        mbar_wait(&kv_full[buf], (it >> 1) & 1);
-        for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
-          const int slot = tile_iter & 1;
-          const uint32_t sQ = smem_u32(smem + OFF_Q + slot * Q_TILE_BYTES);
-          const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0;
-          long long tm0 = 0, tm1 = 0, tm2 = 0, tm3 = 0, tm4 = 0, tm5 = 0;
-          if (timing) tm0 = clock64();
-          mbar_wait(&q_full[slot], (tile_iter >> 1) & 1);
-          if (timing) tm1 = clock64();
-          mbar_wait(s_empty, (tile_iter & 1) ^ 1);
-          tc_fence_after();
-          if (timing) tm2 = clock64();
-          // ---- S = Q_t K^T
-          const uint64_t q_desc = umma_smem_desc_sw128(sQ, 16, 1024);
-          const uint64_t k_desc1 = umma_smem_desc_sw128(sK, 16, 1024);
-          const uint64_t k_desc2 = umma_smem_desc_sw128(sK + 256 * ROW_BYTES, 16, 1024);
+      int part_n[3], part_last_chunk[3];   // key count of each part, last 64-key P chunk that lives in its columns
+      uint32_t idesc_s[3];
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            umma_bf16_ss(tmem_base + S_COL, q_desc + uint64_t(2 * k), k_desc1 + uint64_t(2 * k), idesc_s1, k != 0);
-            if (n2 > 0)
-              umma_bf16_ss(tmem_base + S_COL + 256, q_desc + uint64_t(2 * k), k_desc2 + uint64_t(2 * k), idesc_s2,
-                           k != 0);
-          }
-          umma_commit(s_full);
-          umma_commit(&q_empty[slot]);
-          // ---- O = P V, P read from TMEM as the softmax warps store it, chunk by chunk
-          if (timing) tm3 = clock64();
-          mbar_wait(o_empty, (tile_iter & 1) ^ 1);
+      for (int i = 0; i < 3; ++i) {
+        const int end = (i + 1) * S_PART < tpad ? (i + 1) * S_PART : tpad;
+        part_n[i] = end - i * S_PART > 0 ? end - i * S_PART : 0;
+        part_last_chunk[i] = (end + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS - 1;
+        idesc_s[i] = umma_idesc_bf16(QT, part_n[i] > 0 ? part_n[i] : 16, 0, 0);
+      }
+      const int my_pairs = (npairs - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+      const uint32_t ntiles = uint32_t(my_pairs) * uint32_t(tiles_per_pair);
+      // descriptor of (slot / buffer 0, offset 0); a byte offset adds (offset >> 4) to the start-address field
+      const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(smem + OFF_Q), 16, 1024);
+      const uint64_t k_desc0 = umma_smem_desc_sw128(smem_u32(smem + OFF_K), 16, 1024);
+      const uint64_t v_desc0 = umma_smem_desc_sw128(smem_u32(smem + OFF_V), 1024, 1024);
+      // S = Q_g K^T for one key part of tile g (pair iteration `it`, tile `t`) of this CTA.  Tensor-core work executes
+      // in issue order, so a part may be issued as soon as the P.V steps reading the P in its columns have been issued.
+      auto issue_s = [&](uint32_t g, int it, int t, int part) {
+        const int buf = it & 1, slot = g & 1;
+        if (part == 0) {
+          if (t == 0) mbar_wait(&kv_full[buf], (it >> 1) & 1);
+          mbar_wait(&q_full[slot], (g >> 1) & 1);
           tc_fence_after();
-          if (timing) tm4 = clock64();
-          for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(&p_full[c], tile_iter & 1);
+        }
+        const uint64_t q_desc = q_desc0 + uint64_t(slot * (Q_TILE_BYTES >> 4));
+        const uint64_t k_desc = k_desc0 + uint64_t(buf * (KV_BYTES >> 4) + part * ((S_PART * ROW_BYTES) >> 4));
+        const uint32_t d = tmem_base + S_COL + part * S_PART;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(d, q_desc + uint64_t(2 * k), k_desc + uint64_t(2 * k), idesc_s[part], k != 0);
+        umma_commit(&s_full[part]);
+        // empty parts (short token counts) complete together with the last real one; so does the Q slot
+#pragma unroll
+        for (int nx = part + 1; nx <= 3; ++nx) {
+          if (nx < 3 && part_n[nx] > 0) break;
+          if (nx < 3) umma_commit(&s_full[nx]);
+          else        umma_commit(&q_empty[slot]);
+        }
+      };
+      if (ntiles > 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (part_n[i] > 0) issue_s(0, 0, 0, i);
+      }
+      int it = 0, t = 0;
+      for (uint32_t g = 0; g < ntiles; ++g) {
+        int nit = it, nt = t + 1;            // coordinates of tile g + 1
+        if (nt == tiles_per_pair) { nt = 0; ++nit; }
+        const bool has_next = g + 1 < ntiles;
+        const int buf = it & 1;
+        const uint32_t ob = g & 1;
+        const uint64_t v_desc = v_desc0 + uint64_t(buf * (KV_BYTES >> 4));
+        const uint32_t d_o = tmem_base + O_COL + ob * HD;
+        // ---- O[ob] = P V, P read from TMEM as the softmax warps store it, chunk by chunk
+        mbar_wait(&o_empty[ob], ((g >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+          if (c < nchunks) {
+            mbar_wait(&p_full[c], g & 1);
             tc_fence_after();
-            const int keys = (tpad - c * 64) < 64 ? (tpad - c * 64) : 64;
-            for (int k = 0; k < keys / 16; ++k) {
+            if (TIMING && p.dbg != nullptr && blockIdx.x == 0 && g == 10) p.dbg[16 + c] = clock64();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
               const int key0 = c * 64 + k * 16;
-              const uint64_t v_desc = umma_smem_desc_sw128(sV + uint32_t(key0) * ROW_BYTES, 1024, 1024);
-              umma_bf16_ts(tmem_base + O_COL, tmem_base + P_COL + uint32_t(key0 >> 1), v_desc, idesc_pv, key0 != 0);
+              if (key0 < tpad) {
+                // P of keys [key0, key0+16): 8 packed columns at the start of the 32-column logit group they came from
+                const uint32_t pcol = uint32_t((key0 & ~31) + ((key0 & 16) >> 1));
+                umma_bf16_ts(d_o, tmem_base + S_COL + pcol, v_desc + uint64_t(key0 * (ROW_BYTES >> 4)), idesc_pv, key0 != 0);
+              }
+            }
+            if (c == nchunks - 1) {
+              umma_commit(&o_full[ob]);
+              if (t == tiles_per_pair - 1) umma_commit(&kv_empty[buf]);
+            }
+            if (has_next) {   // logits of the next tile for the key parts whose columns are now free
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                if (part_n[i] > 0 && c == part_last_chunk[i]) {
+                  issue_s(g + 1, nit, nt, i);
+                  if (TIMING && p.dbg != nullptr && blockIdx.x == 0 && g == 10) p.dbg[24 + i] = clock64();
+                }
             }
           }
-          umma_commit(o_full);
-          if (timing) {
-            tm5 = clock64();
-            p.dbg[8] += tm1 - tm0; p.dbg[9] += tm2 - tm1; p.dbg[10] += tm3 - tm2; p.dbg[11] += tm4 - tm3;
-            p.dbg[12] += tm5 - tm4;
-          }
         }
-        umma_commit(&kv_empty[buf]);
+        it = nit; t = nt;
       }
     }
   } else if (warp >= 4 && warp < 4 + NUM_SOFTMAX_WARPS) {
@@ -233,19 +268,94 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int r = q * 32 + lane;         // row inside the tile
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* out_stage = smem + OFF_OST + (warp - 4) * 2048;  // 32 rows x 64 B, source of this warp's bulk stores
-    uint32_t tile_iter = 0;
+    const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const bool stamping = TIMING && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;   // warps 4 and 8
+    long long* stamp = p.dbg + 32 + hf * 16;
+    long long tepi = 0;
+
+    // Normalise and store tile gp (image b, head h, query tile t) from O[gp & 1].  Runs one tile late, between two
+    // exponential chunks of tile gp + 1 (or after the loop for the last tile): by then P.V of tile gp has long finished,
+    // and its latencies (TMEM load, staging, bulk store) hide under the other warp's exponentials.
+    auto epilogue = [&](uint32_t gp, int b, int h, int t) {
+      long long te0 = 0;
+      if (timing) te0 = clock64();
+      const uint32_t ob = gp & 1;
+      const float l = xch_sum[ob * 256 + r] + xch_sum[ob * 256 + 128 + r];
+      const bool warp_active = kAllRowsLive || t * QT + q * 32 < T - n_tail;        // any query row of this warp in the tile
+      const bool full_rows = kAllRowsLive || t * QT + q * 32 + 32 <= T - n_tail;    // all 32 rows of this warp are queries
+      const int tok = t * QT + r;
+      if (full_rows) {
+        if (lane == 0) tma_store_wait_read();   // the previous tile's bulk store has finished reading the staging tile
+        __syncwarp();
+      }
+      mbar_wait(&o_full[ob], (gp >> 1) & 1);
+      tc_fence_after();
+      if (timing) p.dbg[8] += clock64() - te0;
+      uint32_t o[32];
+      if (warp_active) {
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + ob * HD + hf * 32, o);
+        tmem_ld_wait();
+      }
+      if (timing) p.dbg[9] += clock64() - te0;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
+      if (warp_active && (full_rows || tok < T - n_tail)) {
+        const float inv = 1.0f / l;
+        uint4 w[4];
+#pragma unroll
+        for (int jv = 0; jv < 4; ++jv) {
+          w[jv].x = pack_bf16x2(__uint_as_float(o[jv * 8 + 0]) * inv, __uint_as_float(o[jv * 8 + 1]) * inv);
+          w[jv].y = pack_bf16x2(__uint_as_float(o[jv * 8 + 2]) * inv, __uint_as_float(o[jv * 8 + 3]) * inv);
+          w[jv].z = pack_bf16x2(__uint_as_float(o[jv * 8 + 4]) * inv, __uint_as_float(o[jv * 8 + 5]) * inv);
+          w[jv].w = pack_bf16x2(__uint_as_float(o[jv * 8 + 6]) * inv, __uint_as_float(o[jv * 8 + 7]) * inv);
+        }
+        if (full_rows) {
+          // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
+#pragma unroll
+          for (int jv = 0; jv < 4; ++jv)
+            *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((jv ^ ((lane >> 1) & 3)) << 4)) = w[jv];
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * T + tok) * (p.H * HD) + h * HD + hf * 32);
+#pragma unroll
+          for (int jv = 0; jv < 4; ++jv) dst[jv] = w[jv];
+        }
+      }
+      if (timing) p.dbg[10] += clock64() - te0;
+      if (full_rows) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, out_stage, h * HD + hf * 32, b * T + t * QT + q * 32);  // 32 rows x 32 columns
+          tma_store_commit();
+        }
+      }
+      if (timing) tepi += clock64() - te0;
+    };
+
+    uint32_t g = 0;                      // tile counter of this CTA
+    int pb = 0, ph = 0, pt = 0;          // coordinates of tile g - 1 (its epilogue is still owed)
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int b = pair / p.H, h = pair - b * p.H;
-      for (int t = 0; t < tiles_per_pair; ++t, ++tile_iter) {
-        const uint32_t par = tile_iter & 1;
-        const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
-        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0, tk6 = 0;
-        if (timing) tk0 = clock64();
-        mbar_wait(s_full, par);
+      for (int t = 0; t < tiles_per_pair; ++t, ++g) {
+        const uint32_t par = g & 1;
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
+        if (timing) { tk0 = clock64(); tepi = 0; }
+        if (stamping && g == 11) stamp[0] = clock64();
+        mbar_wait(&s_full[0], par);
         tc_fence_after();
+        if (stamping && g == 11) stamp[1] = clock64();
         if (timing) tk1 = clock64();
+        int parts_ready = 1;             // the key parts of S arrive on their own barriers, in order
+        auto need_part = [&](int part) {
+          while (parts_ready <= part) {
+            mbar_wait(&s_full[parts_ready], par);
+            tc_fence_after();
+            if (stamping && g == 11) stamp[1 + parts_ready] = clock64();
+            ++parts_ready;
+          }
+        };
         const bool warp_active = kAllRowsLive || t * QT + q * 32 < T - n_tail;  // any query row of this warp in the tile
-        const int tok = t * QT + r;
         // Key columns are dealt in 64-column chunks: chunk c of this warp = columns [64c + 32hf, +32) (the last one
         // may hold 16).  In the specialised instance both passes are software pipelined: the TMEM load of chunk c+1
         // is in flight while chunk c is reduced / exponentiated (two register buffers, chunk loop unrolled by hand).
@@ -268,6 +378,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         float m = -INFINITY;
         auto max_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
           if (!chunk_exists(c)) return;
+          need_part(((kPrefetch ? c + 1 : c) * 64) / S_PART < 2 ? ((kPrefetch ? c + 1 : c) * 64) / S_PART : 2);
           if (!kPrefetch) { issue_ld(c, cur); tmem_ld_wait(); }
           const bool more = kPrefetch && chunk_exists(c + 1);
           if (more) issue_ld(c + 1, nxt);
@@ -278,15 +389,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         };
         if (kPrefetch && chunk_exists(0)) { issue_ld(0, va); tmem_ld_wait(); }
         max_step(0, va, vb); max_step(1, vb, va); max_step(2, va, vb); max_step(3, vb, va); max_step(4, va, vb);
+        need_part(2);   // (every tile consumes one phase of all three barriers, whatever its chunk count)
+        if (stamping && g == 11) stamp[4] = clock64();
         if (timing) tk2 = clock64();
         if (kPrefetch && chunk_exists(0)) issue_ld(0, va);  // pass 2's first chunk travels during the max exchange
-        xch_max[hf * 128 + r] = m;
+        // exchange buffers alternate with the tile parity: the partner warp may already be a phase ahead, and the
+        // row sums written at the end of this tile are read one tile later (deferred epilogue)
+        xch_max[par * 256 + hf * 128 + r] = m;
         named_bar_sync(1 + q, 64);
-        m = fmaxf(xch_max[r], xch_max[128 + r]);
+        m = fmaxf(xch_max[par * 256 + r], xch_max[par * 256 + 128 + r]);
         const float msl = m * p.sl2;
         if (kPrefetch && chunk_exists(0)) tmem_ld_wait();
         if (timing) tk3 = clock64();
-        // ---- pass 2: exponentials, row sum, bf16 P into TMEM
+        // ---- pass 2: exponentials, row sum, bf16 P into TMEM over the logits just consumed
         float l = 0.f;
         auto exp_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
           if (c >= nchunks) return;
@@ -296,79 +411,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (have) {
             const int c0 = c * 64 + hf * 32;
             uint32_t pk[16];
-            if (c0 + 32 <= T) l += exp_group<false>(cur, p.sl2, msl, 32, pk);
-            else                l += exp_group<true>(cur, p.sl2, msl, T - c0, pk);
+            if (c0 + 32 <= T) l += exp_group<false, POLY>(cur, p.sl2, msl, 32, pk);
+            else                l += exp_group<true, POLY>(cur, p.sl2, msl, T - c0, pk);
             if (tpad - c0 >= 32) {
-              tmem_st_32x32b_x16(tmem_base + lane_addr + P_COL + (c0 >> 1), pk);
+              tmem_st_32x32b_x16(tmem_base + lane_addr + S_COL + c0, pk);
             } else {
-              tmem_st_32x32b_x8(tmem_base + lane_addr + P_COL + (c0 >> 1), *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
+              tmem_st_32x32b_x8(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
             }
           }
           if (more) tmem_ld_wait();
           if (have) tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (c == nchunks - 1 && lane == 0) mbar_arrive(s_empty);  // all S reads of this warp are done
           if (lane == 0) mbar_arrive(&p_full[c]);
+          if (stamping && g == 10) stamp[8 + c] = clock64();
         };
-        exp_step(0, va, vb); exp_step(1, vb, va); exp_step(2, va, vb); exp_step(3, vb, va); exp_step(4, va, vb);
-        if (timing) tk4 = clock64();
-        xch_sum[hf * 128 + r] = l;
-        named_bar_sync(1 + q, 64);
-        l = xch_sum[r] + xch_sum[128 + r];
-        if (timing) tk5 = clock64();
-        // ---- epilogue: this warp normalises 32 of the 64 output columns
-        const bool full_rows = kAllRowsLive || t * QT + q * 32 + 32 <= T - n_tail;   // all 32 rows of this warp are queries
-        if (full_rows) {
-          if (lane == 0) tma_store_wait_read();   // the previous tile's bulk store has finished reading the staging tile
-          __syncwarp();
-        }
-        mbar_wait(o_full, par);
-        tc_fence_after();
-        if (timing) tk6 = clock64();
-        uint32_t o[32];
-        if (warp_active) {
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, o);
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-        if (warp_active && (full_rows || tok < T - n_tail)) {
-          const float inv = 1.0f / l;
-          uint4 w[4];
-#pragma unroll
-          for (int jv = 0; jv < 4; ++jv) {
-            w[jv].x = pack_bf16x2(__uint_as_float(o[jv * 8 + 0]) * inv, __uint_as_float(o[jv * 8 + 1]) * inv);
-            w[jv].y = pack_bf16x2(__uint_as_float(o[jv * 8 + 2]) * inv, __uint_as_float(o[jv * 8 + 3]) * inv);
-            w[jv].z = pack_bf16x2(__uint_as_float(o[jv * 8 + 4]) * inv, __uint_as_float(o[jv * 8 + 5]) * inv);
-            w[jv].w = pack_bf16x2(__uint_as_float(o[jv * 8 + 6]) * inv, __uint_as_float(o[jv * 8 + 7]) * inv);
-          }
-          if (full_rows) {
-            // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
-#pragma unroll
-            for (int jv = 0; jv < 4; ++jv)
-              *reinterpret_cast<uint4*>(out_stage + lane * 64 + ((jv ^ ((lane >> 1) & 3)) << 4)) = w[jv];
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(b) * T + tok) * (p.H * HD) + h * HD + hf * 32);
-#pragma unroll
-            for (int jv = 0; jv < 4; ++jv) dst[jv] = w[jv];
-          }
-        }
-        if (full_rows) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, out_stage, h * HD + hf * 32, b * T + t * QT + q * 32);  // 32 rows x 32 columns
-            tma_store_commit();
-          }
-        }
+        // the two warps of a scheduler take the owed epilogue at different chunks: while one sits in its latencies the
+        // other keeps the MUFU busy
+        exp_step(0, va, vb);
+        if (g > 0 && hf == 0) epilogue(g - 1, pb, ph, pt);
+        exp_step(1, vb, va); exp_step(2, va, vb);
+        if (g > 0 && hf == 1) epilogue(g - 1, pb, ph, pt);
+        exp_step(3, vb, va); exp_step(4, va, vb);
+        xch_sum[par * 256 + hf * 128 + r] = l;
+        pb = b; ph = h; pt = t;
         if (timing) {
-          const long long tk7 = clock64();
-          p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3;
-          p.dbg[4] += tk5 - tk4; p.dbg[5] += tk6 - tk5; p.dbg[6] += tk7 - tk6; p.dbg[7] += 1;
+          tk4 = clock64();
+          p.dbg[0] += tk1 - tk0; p.dbg[1] += tk2 - tk1; p.dbg[2] += tk3 - tk2; p.dbg[3] += tk4 - tk3 - tepi;
+          p.dbg[6] += tepi; p.dbg[7] += 1;
         }
       }
+    }
+    if (g > 0) {
+      named_bar_sync(1 + q, 64);           // the partner's row sums of the last tile
+      epilogue(g - 1, pb, ph, pt);
     }
     if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the bulk stores reading it
   } else if (warp >= 4 + NUM_SOFTMAX_WARPS && n_tail > 0) {
@@ -528,22 +604,24 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   p.dbg = getenv("FP_ATTN_DBG") ? reinterpret_cast<long long*>(strtoull(getenv("FP_ATTN_DBG"), nullptr, 0)) : nullptr;
   p.nchunks = (tpad + P_CHUNK_KEYS - 1) / P_CHUNK_KEYS;
   p.sl2 = scale * 1.4426950408889634f;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(attention_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FP_CUDA(cudaFuncSetAttribute(attention_kernel<false, 261>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FP_CUDA(cudaFuncSetAttribute(attention_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FP_CUDA(cudaFuncSetAttribute(attention_kernel<true, 261>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
   const int npairs = B * H;
   const int grid = npairs < sm_count() ? npairs : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
   const bool special = T == 261 && !getenv("FP_ATTN_GENERIC");  // 224^2 crops: (224/14)^2 + 5 tokens
-  if (p.dbg && special) attention_kernel<true, 261><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
-  else if (p.dbg)    attention_kernel<true, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
-  else if (special)  attention_kernel<false, 261><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
-  else               attention_kernel<false, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);
+  // POLY = 0: every exponential on the MUFU.  Moving 25-50 % of them to the FMA pipe (ex2_poly_x2) was measured and
+  // does not help: the softmax warps are bound by TMEM reads and latency, not by the 16-lane MUFU (0.297 ms with or
+  // without at B=521, T=261; 0.309 / 0.324 ms at 37.5 / 50 %).
+#define FP_LAUNCH_ATTN_POLY(TIMING_, TC_)                                                                            \
+  do {                                                                                                               \
+    auto kern = attention_kernel<TIMING_, TC_, 0u>;                                                                  \
+    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                    \
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);                                      \
+  } while (0)
+  if (p.dbg && special) FP_LAUNCH_ATTN_POLY(true, 261);
+  else if (p.dbg)       FP_LAUNCH_ATTN_POLY(true, 0);
+  else if (special)     FP_LAUNCH_ATTN_POLY(false, 261);
+  else                  FP_LAUNCH_ATTN_POLY(false, 0);
+#undef FP_LAUNCH_ATTN_POLY
   FP_CUDA(cudaGetLastError());
   return 0;
 }

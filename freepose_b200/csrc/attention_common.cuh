@@ -77,10 +77,36 @@ __device__ __forceinline__ unsigned long long add_f2(unsigned long long a, unsig
   return r;
 }
 
+// 2^y for two values on the FMA / integer pipes (no MUFU): y is clamped to >= -125, split into round(y) + f with
+// f in [-0.5, 0.5] (magic-number rounding), 2^f by a degree-4 minimax polynomial (max relative error 2.7e-6, i.e. 1/700
+// of a bf16 ulp -- ex2.approx itself is good to 2^-22), and round(y) is added into the exponent field.  Used for a fixed
+// subset of the softmax exponentials so that the 16-lane MUFU is not the only unit working (the FlashAttention-4 trick).
+__device__ __forceinline__ void ex2_poly_x2(float y0, float y1, float& e0, float& e1) {
+  const unsigned long long y = pack_f2(fmaxf(y0, -125.0f), fmaxf(y1, -125.0f));
+  const unsigned long long t = add_f2(y, pack_f2(12582912.0f, 12582912.0f));            // 1.5 * 2^23: low bits = round(y)
+  const unsigned long long n = add_f2(t, pack_f2(-12582912.0f, -12582912.0f));
+  const unsigned long long f = fma_f2(n, pack_f2(-1.0f, -1.0f), y);
+  unsigned long long q = fma_f2(pack_f2(0.009570101276040077f, 0.009570101276040077f), f,
+                                pack_f2(0.05591785907745361f, 0.05591785907745361f));
+  q = fma_f2(q, f, pack_f2(0.240247443318367f, 0.240247443318367f));
+  q = fma_f2(q, f, pack_f2(0.6931217908859253f, 0.6931217908859253f));
+  q = fma_f2(q, f, pack_f2(0.9999992847442627f, 0.9999992847442627f));
+  float t0, t1, q0, q1;
+  unpack_f2(t, t0, t1);
+  unpack_f2(q, q0, q1);
+  e0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+// Which of the 16 (even, odd) column pairs of a 32-logit group take the polynomial instead of MUFU.
+#ifndef FP_ATTN_POLY_MASK
+#define FP_ATTN_POLY_MASK 0x0000u
+#endif
+
 // exponentials of 32 logits -> 16 packed bf16x2 words; returns the fp32 sum of the unrounded values.
 // MASKED: columns >= valid are forced to 0 (only the group that straddles T takes this path).
 // Packed f32x2 FMA / ADD: 2.5 issue slots per element (FFMA2 .5, MUFU 1, FADD2 .5, F2FP .5) instead of 3.5.
-template <bool MASKED>
+template <bool MASKED, unsigned POLY = FP_ATTN_POLY_MASK>
 __device__ __forceinline__ float exp_group(const uint32_t (&v)[32], float sl2, float msl, int valid,
                                            uint32_t (&packed)[16]) {
   const unsigned long long sl2_2 = pack_f2(sl2, sl2), nmsl_2 = pack_f2(-msl, -msl);
@@ -89,7 +115,13 @@ __device__ __forceinline__ float exp_group(const uint32_t (&v)[32], float sl2, f
   for (int j = 0; j < 32; j += 2) {
     float y0, y1;
     unpack_f2(fma_f2(pack_f2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2_2, nmsl_2), y0, y1);
-    float e0 = ex2(y0), e1 = ex2(y1);
+    float e0, e1;
+    if ((POLY >> (j >> 1)) & 1u) {
+      ex2_poly_x2(y0, y1, e0, e1);
+    } else {
+      e0 = ex2(y0);
+      e1 = ex2(y1);
+    }
     if (MASKED) {
       e0 = j < valid ? e0 : 0.f;
       e1 = j + 1 < valid ? e1 : 0.f;

@@ -119,7 +119,7 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {   // (see attention.cu: a single elected thread lets the compiler emit UTCHMMA back to back)
       const uint32_t idesc_pv = umma_idesc_bf16(QT, HD, 0, 1);
       uint32_t kvi = 0, qi = 0, blk_iter = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++qi) {

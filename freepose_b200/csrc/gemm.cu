@@ -321,7 +321,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (elect.sync, not `lane == 0`: the compiler then knows a single thread is active and emits the UTCHMMA stream
+    // back to back instead of wrapping every instruction in an elect / branch loop)
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -458,7 +460,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM2, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;

@@ -1,19 +1,55 @@
-"""Dev aid: per-phase cycle counters of the attention kernel (softmax warp 4 and the MMA warp of CTA 0)."""
-import os, sys, torch
+"""Developer aid (not a pytest file): per-phase cycle counters of the attention kernel's TIMING instance.
+Run:  gpurun -- python tests/dev_attn_phases.py"""
+import os
+import sys
+
+import torch
+
 sys.path.insert(0, ".")
-from freepose_b200 import ops
-B = int(os.environ.get("ATTN_B", "521"))
-T = int(sys.argv[1]) if len(sys.argv) > 1 else 261
+from freepose_b200 import ops  # noqa: E402
+
+B, T = 521, 261
+torch.manual_seed(0)
 qkv = torch.randn(B * T, 3072, device="cuda").to(torch.bfloat16)
-for _ in range(3): ops.attention(qkv, B, T)
-dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+for _ in range(2):
+    ops.attention(qkv, B, T)
+torch.cuda.synchronize()
 os.environ["FP_ATTN_DBG"] = str(dbg.data_ptr())
 ops.attention(qkv, B, T)
 torch.cuda.synchronize()
 del os.environ["FP_ATTN_DBG"]
 d = dbg.cpu().tolist()
 n = max(d[7], 1)
-names = ["sm wait s_full", "sm pass1", "sm max xchg", "sm pass2", "sm sum xchg", "sm wait o_full", "sm epilogue", "tiles",
-         "mma wait q_full", "mma wait s_empty", "mma S issue", "mma wait o_empty", "mma PV (p_full waits)"]
-for i, nm in enumerate(names):
-    print("%-24s %10.0f cycles/tile" % (nm, d[i] / n if i != 7 else d[i]))
+names = {0: "wait s_full", 1: "pass1 max", 2: "max exchange", 3: "pass2 exp", 6: "deferred epilogue"}
+print("softmax warp 4 of CTA 0, cycles per tile over", n, "tiles")
+for k, v in names.items():
+    print(f"  {v:18s} {d[k] / n:8.1f}")
+print("  total              %8.1f" % (sum(d[k] for k in names) / n))
+print("  epilogue cumulative: waits %.1f, +O load %.1f, +scale/stage %.1f" % (d[8] / n, d[9] / n, d[10] / n))
+t0 = d[16]
+rel = lambda v: v - t0 if v else None
+print("timeline around tile 10 -> 11 of CTA 0 (cycles, relative to the MMA thread seeing p_full[0] of tile 10)")
+print("  MMA sees p_full[c] (tile 10):      ", [rel(v) for v in d[16:21]])
+print("  MMA issued part i of tile 11:      ", [rel(v) for v in d[24:27]])
+for hf in (0, 1):
+    s0 = 32 + 16 * hf
+    print(f"  warp hf={hf}: arrives p_full[c] (t10): ", [rel(v) for v in d[s0 + 8:s0 + 13]])
+    print(f"  warp hf={hf}: tile 11 start, parts A/B/C seen, pass1 end: ", [rel(v) for v in d[s0:s0 + 5]])
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+ms = timeit(lambda: ops.attention(qkv, B, T))
+print(f"attention B={B} T={T}: {ms:.3f} ms  {4 * B * 16 * T * T * 64 / ms / 1e9:.1f} TFLOP/s")

@@ -118,7 +118,9 @@ def test_layernorm(ops):
     check_stage(out, contract_layernorm(x.float(), w.float(), b.float(), 1e-6), "layernorm")
 
 
-@pytest.mark.parametrize("B,T", [(2, 261), (1, 17), (3, 272), (2, 256), (5, 128), (1, 129)])
+@pytest.mark.parametrize("B,T", [(2, 261), (1, 17), (3, 272), (2, 256), (5, 128), (1, 129),
+                                 # several (image, head) pairs per CTA: the cross-tile / cross-pair pipeline
+                                 (40, 261), (30, 140), (24, 200), (40, 40), (21, 264)])
 def test_attention(ops, B, T):
     from oracle.vit import contract_attention
     torch.manual_seed(T)
