@@ -136,7 +136,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------- TMA loader
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       uint32_t qi = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
@@ -285,7 +285,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool full_rows = kAllRowsLive || t * QT + q * 32 + 32 <= T - n_tail;    // all 32 rows of this warp are queries
       const int tok = t * QT + r;
       if (full_rows) {
-        if (lane == 0) tma_store_wait_read();   // the previous tile's bulk store has finished reading the staging tile
+        tma_store_wait_read();   // the previous tile's bulk store has finished reading the staging tile
         __syncwarp();
       }
       mbar_wait(&o_full[ob], (gp >> 1) & 1);
@@ -325,7 +325,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (full_rows) {
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d(&tmOut, out_stage, h * HD + hf * 32, b * T + t * QT + q * 32);  // 32 rows x 32 columns
           tma_store_commit();
         }
@@ -446,7 +446,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       named_bar_sync(1 + q, 64);           // the partner's row sums of the last tile
       epilogue(g - 1, pb, ph, pt);
     }
-    if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the bulk stores reading it
+    tma_store_wait_all();  // the staging tile must outlive the bulk stores reading it
   } else if (warp >= 4 + NUM_SOFTMAX_WARPS && n_tail > 0) {
     // ---------------------------------------------------------------------------- tail queries (<= 8 rows)
     // Warp-level mma.sync.m16n8k16 on the K/V tiles already in shared memory (ldmatrix understands the TMA 128B

@@ -92,7 +92,7 @@ attention_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------- TMA loader
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t kvi = 0, qi = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++qi) {
         const int pair = item / p.nq, t = item - pair * p.nq;

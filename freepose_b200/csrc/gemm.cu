@@ -237,7 +237,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
     }
     if (kTmaStore) {
       // only now must the previous chunk's bulk store have finished reading the staging tile
-      if (lane == 0) tma_store_wait_read();
+      tma_store_wait_read();   // (a no-op for the lanes that never committed a bulk group)
       __syncwarp();
       // 64-byte swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk i of row `lane` sits at chunk i ^ ((lane>>1)&3)
 #pragma unroll
@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
     if (kTmaStore) {
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && p.debug != 1) {
+      if (p.debug != 1 && elect_one()) {
         tma_store_2d(tmOut, out_stage, gcol, row - lane);  // box = 32 rows of this warp's lane quarter x 32 columns
         tma_store_commit();
       }
@@ -305,7 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -373,7 +373,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
-  if (warp >= 4 && lane == 0) tma_store_wait_all();  // smem staging must outlive the bulk stores reading it
+  if (warp >= 4) tma_store_wait_all();  // smem staging must outlive the bulk stores reading it
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -439,7 +439,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -509,7 +509,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
-  if (warp >= 4 && lane == 0) tma_store_wait_all();
+  if (warp >= 4) tma_store_wait_all();
   tc_fence_before();
   cluster_sync_all();  // the peer may still be signalling barriers / reading operands that live in this CTA
   if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
