@@ -37,7 +37,8 @@ class RasterArgs(C.Structure):
                 ("F", C.c_int), ("poses", C.c_void_p), ("B", C.c_int), ("fx", C.c_float), ("fy", C.c_float),
                 ("cx", C.c_float), ("cy", C.c_float), ("res", C.c_int), ("msaa", C.c_int),
                 ("cull_backfaces", C.c_int), ("gamma_lut", C.c_void_p), ("rgb", C.c_void_p),
-                ("depth", C.c_void_p)]
+                ("depth", C.c_void_p), ("primitive", C.c_int), ("uv", C.c_void_p), ("texture", C.c_void_p),
+                ("tex_w", C.c_int), ("tex_h", C.c_int), ("tex_levels", C.c_int), ("srgb_lut", C.c_void_p)]
 
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -95,7 +96,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.fp_abi_version() != 1:
+    if lib.fp_abi_version() != 2:
         raise RuntimeError("libfreepose_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -110,9 +110,7 @@ def synthetic_frame(meshes, h=480, w=640, seed=0, device="cuda"):
         pose = np.eye(4)
         pose[:3, :3] = q
         pose[:3, 3] = [rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(2.2, 3.0)]
-        from .pipeline.utils import mesh_to_device
-        v, fc, c = mesh_to_device(mesh, torch.device(device))
-        rgb, depth = ops.rasterize(v, fc, c, torch.from_numpy(pose[None]).float().to(device), f, f, w / 2, h / 2, side)
+        rgb, depth = ops.rasterize_mesh(mesh, torch.from_numpy(pose[None]).float().to(device), f, f, w / 2, h / 2, side)
         rgb, depth = rgb[0, :h, :w].cpu().numpy(), depth[0, :h, :w].cpu().numpy()
         m = depth > 0
         if m.sum() < 50:

@@ -131,6 +131,8 @@ FP_API int fp_rasterize(const fp_raster_args* g, void* workspace, size_t workspa
   a.poses = g->poses; a.B = g->B; a.fx = g->fx; a.fy = g->fy; a.cx = g->cx; a.cy = g->cy;
   a.res = g->res; a.msaa = g->msaa; a.cull_backfaces = g->cull_backfaces; a.gamma_lut = g->gamma_lut;
   a.rgb = g->rgb; a.depth = g->depth;
+  a.primitive = g->primitive; a.uv = g->uv; a.texture = g->texture;
+  a.tex_w = g->tex_w; a.tex_h = g->tex_h; a.tex_levels = g->tex_levels; a.srgb_lut = g->srgb_lut;
   return fp::rasterize(a, workspace, workspace_bytes, S(stream));
 }
 

@@ -92,7 +92,7 @@ int softvote_mean(const float* acc, float* out, long long n, int frames, cudaStr
 struct RasterArgs {
   const float* verts;     // [V, 3] fp32 object-space
   const int32_t* faces;   // [F, 3]
-  const uint8_t* colors;  // [V, 3] u8 vertex colours
+  const uint8_t* colors;  // [V, 3] u8 vertex colours (may be null when a texture is given)
   int V, F;
   const float* poses;     // [B, 12] row-major 3x4 (R | t), object -> OpenCV camera
   int B;
@@ -102,7 +102,12 @@ struct RasterArgs {
   int cull_backfaces;
   const uint8_t* gamma_lut;  // [65536] u8
   uint8_t* rgb;           // [B, res, res, 3] u8
-  float* depth;           // [B, res, res] fp32 metres, 0 = background
+  float* depth;           // [B, res, res] fp32
+  int primitive;          // 0 = triangles, 1 = points (faces ignored)
+  const float* uv;        // [V, 2] fp32 or null
+  const uint8_t* texture; // RGBA8 mip chain or null
+  int tex_w, tex_h, tex_levels;
+  const float* srgb_lut;  // [65536] fp32
 };
 int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes);
 int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);

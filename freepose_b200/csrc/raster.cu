@@ -15,7 +15,13 @@
 // (depth bits, face id), so results are deterministic and the CPU oracle (oracle/raster_ref.c) restates them
 // bit for bit.  All fp32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction).
 //
-// Kernels: clear keys -> vertex transform -> triangle scatter (warp-cooperative for large triangles) ->
+// Surfaces (pyrender material paths): per-vertex colours (trimesh ColorVisuals -> COLOR_0), a base-colour texture
+// (trimesh TextureVisuals -> baseColorTexture: REPEAT wrap, trilinear filtering over a box-filtered mip chain, filtered
+// in the stored sRGB values and linearised with x^2.2 afterwards, as pyrender's mesh.frag does), or both multiplied.
+// trimesh.PointCloud inputs (renderer.py:46-51) are GL points of size 1: a one-pixel square sprite centred on the
+// projected vertex, flat vertex colour, the vertex's own depth.
+//
+// Kernels: clear keys -> vertex transform -> triangle (warp-cooperative for large triangles) or point scatter ->
 // resolve (4 pixels per thread, 12-byte RGB + 16-byte depth vector stores).
 #include "common.cuh"
 #include "kernels.h"
@@ -210,44 +216,182 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   }
 }
 
-// Shade triangle `face` at the centre of pixel (px, py): perspective-correct vertex-colour interpolation,
-// x2 ambient, gamma LUT -> unorm8.
+// GL_POINTS with point size 1 (pyrender.Mesh.from_points): the sprite is the square [x - 0.5, x + 0.5) x [y - 0.5, y + 0.5)
+// around the projected vertex; every sample inside it takes the vertex depth.  Key payload = vertex index.
+template <int S>
+__global__ void __launch_bounds__(256)
+point_kernel(const ScreenVertex* __restrict__ sv, unsigned long long* __restrict__ keys, int V, int res) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const ScreenVertex v = sv[size_t(b) * V + i];
+  if (v.x == INT_MIN) return;
+  if (!(v.z > ZNEAR && v.z < ZFAR)) return;
+  unsigned long long* keys_view = keys + size_t(b) * res * res * S;
+  const int x0 = v.x - ONE / 2, y0 = v.y - ONE / 2;       // inclusive lower corner, exclusive upper = +ONE
+  const int pxa = x0 >> SUB, pxb = (x0 + ONE - 1) >> SUB;
+  const int pya = y0 >> SUB, pyb = (y0 + ONE - 1) >> SUB;
+  const unsigned long long key = ((unsigned long long)__float_as_uint(v.z) << 32) | unsigned(i);
+  for (int py = pya; py <= pyb; ++py) {
+    if (py < 0 || py >= res) continue;
+    for (int px = pxa; px <= pxb; ++px) {
+      if (px < 0 || px >= res) continue;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int sx = (px << SUB) + c_sample_off[S == 4][s][0], sy = (py << SUB) + c_sample_off[S == 4][s][1];
+        if (sx >= x0 && sx < x0 + ONE && sy >= y0 && sy < y0 + ONE)
+          atomicMin(&keys_view[(size_t(py) * res + px) * S + s], key);
+      }
+    }
+  }
+}
+
+struct Surface {
+  const uint8_t* colors;    // [V,3] or nullptr
+  const float* uv;          // [V,2] or nullptr
+  const uint8_t* texture;   // RGBA8 mip chain or nullptr
+  const float* srgb_lut;    // [65536] (i/65535)^2.2
+  const uint8_t* gamma_lut; // [65536]
+  int tex_w, tex_h, tex_levels;
+};
+
+// linear colour (already x ambient) -> unorm8 through the gamma LUT
+__device__ __forceinline__ int to_unorm8(float lin, const uint8_t* __restrict__ lut) {
+  lin = fminf(fmaxf(lin, 0.f), 1.f);
+  if (!(lin == lin)) lin = 0.f;
+  return lut[int(__fadd_rn(__fmul_rn(lin, 65535.0f), 0.5f))];
+}
+
+__device__ __forceinline__ int wrap_repeat(int i, int n) {
+  int m = i % n;
+  return m < 0 ? m + n : m;
+}
+
+// One bilinear tap of mip level `lvl` (REPEAT wrap); u, v in texture space with v up (image row 0 is v = 1).
+__device__ __forceinline__ void bilinear(const Surface& sf, int lvl, float u, float v, float out[3]) {
+  size_t off = 0;
+  int W = sf.tex_w, H = sf.tex_h;
+  for (int l = 0; l < lvl; ++l) {
+    off += size_t(W) * H * 4;
+    W = max(1, W >> 1); H = max(1, H >> 1);
+  }
+  const float x = __fadd_rn(__fmul_rn(u, float(W)), -0.5f);
+  const float y = __fadd_rn(__fmul_rn(__fadd_rn(1.0f, -v), float(H)), -0.5f);
+  const float xf = floorf(x), yf = floorf(y);
+  const float fx = __fadd_rn(x, -xf), fy = __fadd_rn(y, -yf);
+  // (coordinates far outside the int range only occur for degenerate UVs; clamp before the conversion)
+  const int ix = int(fminf(fmaxf(xf, -1.0e9f), 1.0e9f)), iy = int(fminf(fmaxf(yf, -1.0e9f), 1.0e9f));
+  const int x0 = wrap_repeat(ix, W), x1 = wrap_repeat(ix + 1, W);
+  const int y0 = wrap_repeat(iy, H), y1 = wrap_repeat(iy + 1, H);
+  const uchar4* t = reinterpret_cast<const uchar4*>(sf.texture + off);
+  const uchar4 c00 = t[size_t(y0) * W + x0], c10 = t[size_t(y0) * W + x1];
+  const uchar4 c01 = t[size_t(y1) * W + x0], c11 = t[size_t(y1) * W + x1];
+  const float a00[3] = {float(c00.x), float(c00.y), float(c00.z)}, a10[3] = {float(c10.x), float(c10.y), float(c10.z)};
+  const float a01[3] = {float(c01.x), float(c01.y), float(c01.z)}, a11[3] = {float(c11.x), float(c11.y), float(c11.z)};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float top = __fadd_rn(a00[ch], __fmul_rn(fx, __fadd_rn(a10[ch], -a00[ch])));
+    const float bot = __fadd_rn(a01[ch], __fmul_rn(fx, __fadd_rn(a11[ch], -a01[ch])));
+    out[ch] = __fadd_rn(top, __fmul_rn(fy, __fadd_rn(bot, -top)));
+  }
+}
+
+// Level of detail from the squared texel footprint rho^2: lambda = log2(rho), with log2 of the mantissa replaced by its
+// chord (lambda = (e + m - 1) / 2 for rho^2 = m * 2^e, m in [1,2)): at most 0.043 levels off, and pure bit arithmetic,
+// so the CPU oracle reproduces it exactly (libm's log2f is not specified to the last bit).
+__device__ __forceinline__ float lod_from_rho2(float rho2, int levels) {
+  const float top = float(levels - 1);
+  if (!(rho2 < 1.0e30f)) return top;
+  if (!(rho2 > 1.0f)) return 0.f;
+  const unsigned bits = __float_as_uint(rho2);
+  const float e = float(int(bits >> 23) - 127);
+  const float m = __fmul_rn(float(bits & 0x7fffffu), 1.1920928955078125e-07f);   // mantissa fraction, exact
+  return fminf(__fmul_rn(0.5f, __fadd_rn(e, m)), top);
+}
+
+// Shade triangle `face` at the centre of pixel (px, py): perspective-correct interpolation of vertex colours and / or
+// texture coordinates, x2 ambient, gamma LUT -> unorm8.  MODE 0 = vertex colours, 1 = texture (times vertex colours
+// when sf.colors is set).
+template <int MODE>
 __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, const int* __restrict__ faces,
-                                      const uint8_t* __restrict__ colors, const uint8_t* __restrict__ lut,
-                                      unsigned face, int px, int py, int out[3]) {
+                                      const Surface& sf, unsigned face, int px, int py, int out[3]) {
   const int i0 = faces[3 * face], i1 = faces[3 * face + 1], i2 = faces[3 * face + 2];
   ScreenVertex v0 = svb[i0], v1 = svb[i1], v2 = svb[i2];
   int c0 = i0, c1 = i1, c2 = i2;
   long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
   if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
-  const long long sx = ((long long)px << SUB) + 128, sy = ((long long)py << SUB) + 128;
-  // unbiased edge values (may be negative: the centre can lie outside a partially covered pixel's triangle)
-  const long long e0 = (long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x);
-  const long long e1 = (long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x);
-  const long long e2 = (long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x);
   const float fa = __ll2float_rn(area);
-  const float w0 = __fmul_rn(__fdiv_rn(__ll2float_rn(e0), fa), v0.iz);
-  const float w1 = __fmul_rn(__fdiv_rn(__ll2float_rn(e1), fa), v1.iz);
-  const float w2 = __fmul_rn(__fdiv_rn(__ll2float_rn(e2), fa), v2.iz);
-  const float wsum = __fadd_rn(__fadd_rn(w0, w1), w2);
+  // perspective weights at (sx, sy) (unbiased edge values: the point may lie outside the triangle)
+  auto weights = [&](long long sx, long long sy, float& w0, float& w1, float& w2, float& wsum) {
+    const long long e0 = (long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x);
+    const long long e1 = (long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x);
+    const long long e2 = (long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x);
+    w0 = __fmul_rn(__fdiv_rn(__ll2float_rn(e0), fa), v0.iz);
+    w1 = __fmul_rn(__fdiv_rn(__ll2float_rn(e1), fa), v1.iz);
+    w2 = __fmul_rn(__fdiv_rn(__ll2float_rn(e2), fa), v2.iz);
+    wsum = __fadd_rn(__fadd_rn(w0, w1), w2);
+  };
+  auto interp = [&](float w0, float w1, float w2, float wsum, float a0, float a1, float a2) {
+    return __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, a0), __fmul_rn(w1, a1)), __fmul_rn(w2, a2)), wsum);
+  };
+  const long long sx = ((long long)px << SUB) + 128, sy = ((long long)py << SUB) + 128;
+  float w0, w1, w2, wsum;
+  weights(sx, sy, w0, w1, w2, wsum);
+  float vc[3] = {255.f, 255.f, 255.f};
+  if (MODE == 0 || sf.colors != nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      vc[ch] = interp(w0, w1, w2, wsum, float(sf.colors[3 * c0 + ch]), float(sf.colors[3 * c1 + ch]),
+                      float(sf.colors[3 * c2 + ch]));
+  }
+  if (MODE == 0) {
+    // base colour in [0,1] is c/255; ambient (2,2,2): linear = 2c/255, clamped; LUT index = round(linear*65535)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(__fmul_rn(vc[ch], 2.0f / 255.0f), sf.gamma_lut);
+    return;
+  }
+  const float ua = sf.uv[2 * c0], ub = sf.uv[2 * c1], uc = sf.uv[2 * c2];
+  const float va = sf.uv[2 * c0 + 1], vb = sf.uv[2 * c1 + 1], vcc = sf.uv[2 * c2 + 1];
+  const float u = interp(w0, w1, w2, wsum, ua, ub, uc), v = interp(w0, w1, w2, wsum, va, vb, vcc);
+  // footprint from the neighbouring pixel centres (the finite differences GL takes inside a 2x2 quad)
+  float x0w, x1w, x2w, xs, y0w, y1w, y2w, ys;
+  weights(sx + ONE, sy, x0w, x1w, x2w, xs);
+  weights(sx, sy + ONE, y0w, y1w, y2w, ys);
+  const float fw = float(sf.tex_w), fh = float(sf.tex_h);
+  const float dux = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, ua, ub, uc), -u), fw);
+  const float dvx = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, va, vb, vcc), -v), fh);
+  const float duy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, ua, ub, uc), -u), fw);
+  const float dvy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, va, vb, vcc), -v), fh);
+  const float rx = __fadd_rn(__fmul_rn(dux, dux), __fmul_rn(dvx, dvx));
+  const float ry = __fadd_rn(__fmul_rn(duy, duy), __fmul_rn(dvy, dvy));
+  const float lod = lod_from_rho2(fmaxf(rx, ry), sf.tex_levels);
+  const int l0 = int(lod);
+  const float t = __fadd_rn(lod, -float(l0));
+  float ca[3];
+  bilinear(sf, l0, u, v, ca);
+  if (t > 0.f) {
+    float cb[3];
+    bilinear(sf, min(l0 + 1, sf.tex_levels - 1), u, v, cb);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) ca[ch] = __fadd_rn(ca[ch], __fmul_rn(t, __fadd_rn(cb[ch], -ca[ch])));
+  }
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    const float a0 = float(colors[3 * c0 + ch]), a1 = float(colors[3 * c1 + ch]), a2 = float(colors[3 * c2 + ch]);
-    float c = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, a0), __fmul_rn(w1, a1)), __fmul_rn(w2, a2)), wsum);
-    // base colour in [0,1] is c/255; ambient (2,2,2): linear = 2c/255, clamped; LUT index = round(linear*65535)
-    float lin = __fmul_rn(c, 2.0f / 255.0f);
-    lin = fminf(fmaxf(lin, 0.f), 1.f);
-    if (!(lin == lin)) lin = 0.f;
-    const int idx = int(__fadd_rn(__fmul_rn(lin, 65535.0f), 0.5f));
-    out[ch] = lut[idx];
+    float cn = __fdiv_rn(ca[ch], 255.0f);
+    cn = fminf(fmaxf(cn, 0.f), 1.f);
+    if (!(cn == cn)) cn = 0.f;
+    float lin = sf.srgb_lut[int(__fadd_rn(__fmul_rn(cn, 65535.0f), 0.5f))];           // sRGB -> linear after filtering
+    if (sf.colors != nullptr) lin = __fmul_rn(lin, __fdiv_rn(vc[ch], 255.0f));         // COLOR_0 multiplier
+    out[ch] = to_unorm8(__fmul_rn(lin, 2.0f), sf.gamma_lut);
   }
 }
 
-template <int S>
+// MODE 0 / 1: triangles (key payload = face), 2: points (key payload = vertex, flat colour)
+template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
-               const int* __restrict__ faces, const uint8_t* __restrict__ colors, const uint8_t* __restrict__ lut,
-               uint8_t* __restrict__ rgb, float* __restrict__ depth, int V, int res) {
+               const int* __restrict__ faces, const Surface sf, uint8_t* __restrict__ rgb, float* __restrict__ depth,
+               int V, int res) {
   const int b = blockIdx.y;
   const int quads_per_row = res >> 2;
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,7 +414,13 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
       if (k[s] != ~0ull) {
         const unsigned face = unsigned(k[s] & 0xffffffffu);
         if (face != last_face) {
-          shade(svb, faces, colors, lut, face, px0 + i, py, col);
+          if (MODE == 2) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+              col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), 2.0f / 255.0f), sf.gamma_lut);
+          } else {
+            shade<MODE>(svb, faces, sf, face, px0 + i, py, col);
+          }
           last_face = face;
         }
         acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2];
@@ -295,6 +445,29 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+template <int S>
+int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* keys, cudaStream_t stream) {
+  Surface sf;
+  sf.colors = a.colors; sf.uv = a.uv; sf.texture = a.texture; sf.srgb_lut = a.srgb_lut; sf.gamma_lut = a.gamma_lut;
+  sf.tex_w = a.tex_w; sf.tex_h = a.tex_h; sf.tex_levels = a.tex_levels;
+  const dim3 rgrid((a.res * a.res / 4 + 255) / 256, a.B);
+  if (a.primitive == 1) {
+    point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res);
+    FP_CUDA(cudaGetLastError());
+    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+  } else {
+    triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res,
+                                                                         a.cull_backfaces);
+    FP_CUDA(cudaGetLastError());
+    if (a.texture != nullptr)
+      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+    else
+      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+  }
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
@@ -307,8 +480,16 @@ int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
 int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   FP_REQUIRE(a.res > 0 && a.res % 4 == 0, "raster: resolution %d must be a positive multiple of 4", a.res);
   FP_REQUIRE(a.msaa == 1 || a.msaa == 4, "raster: msaa must be 1 or 4");
-  FP_REQUIRE(a.V > 0 && a.F > 0, "raster: empty mesh (V=%d, F=%d)", a.V, a.F);
+  FP_REQUIRE(a.primitive == 0 || a.primitive == 1, "raster: primitive must be 0 (triangles) or 1 (points)");
+  FP_REQUIRE(a.V > 0 && (a.primitive == 1 || a.F > 0), "raster: empty mesh (V=%d, F=%d)", a.V, a.F);
   FP_REQUIRE(a.B <= 65535, "raster: at most 65535 views per call");
+  if (a.texture != nullptr) {
+    FP_REQUIRE(a.primitive == 0 && a.uv != nullptr && a.srgb_lut != nullptr, "raster: a texture needs triangles, uv and srgb_lut");
+    FP_REQUIRE(a.tex_w > 0 && a.tex_h > 0 && a.tex_levels > 0 && a.tex_levels <= 16, "raster: bad texture size %dx%d, %d levels",
+               a.tex_w, a.tex_h, a.tex_levels);
+  } else {
+    FP_REQUIRE(a.colors != nullptr, "raster: neither vertex colours nor a texture");
+  }
   if (a.B <= 0) return 0;
   size_t need = 0;
   if (int rc = raster_workspace_bytes(a.B, a.V, a.res, a.msaa, &need)) return rc;
@@ -323,19 +504,7 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
   FP_CUDA(cudaGetLastError());
   vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy);
   FP_CUDA(cudaGetLastError());
-  const dim3 tgrid((a.F + 255) / 256, a.B);
-  const dim3 rgrid((a.res * a.res / 4 + 255) / 256, a.B);
-  if (a.msaa == 4) {
-    triangle_kernel<4><<<tgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces);
-    FP_CUDA(cudaGetLastError());
-    resolve_kernel<4><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, a.colors, a.gamma_lut, a.rgb, a.depth, a.V, a.res);
-  } else {
-    triangle_kernel<1><<<tgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces);
-    FP_CUDA(cudaGetLastError());
-    resolve_kernel<1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, a.colors, a.gamma_lut, a.rgb, a.depth, a.V, a.res);
-  }
-  FP_CUDA(cudaGetLastError());
-  return 0;
+  return a.msaa == 4 ? launch_raster<4>(a, sv, keys, stream) : launch_raster<1>(a, sv, keys, stream);
 }
 
 }  // namespace fp

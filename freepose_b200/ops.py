@@ -202,25 +202,55 @@ def gamma_lut(device) -> torch.Tensor:
     return _gamma_lut_dev[key]
 
 
-def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors: torch.Tensor, poses: torch.Tensor, fx, fy, cx, cy,
-              res: int, msaa: int = 4, cull_backfaces: bool = False):
-    """verts (V,3) fp32, faces (F,3) int32, colors (V,3) u8, poses (B,4,4)|(B,3,4) fp32 -> rgb u8 (B,res,res,3),
-    depth fp32 (B,res,res)."""
+_srgb_lut_dev = {}
+
+
+def srgb_lut(device) -> torch.Tensor:
+    key = str(device)
+    if key not in _srgb_lut_dev:
+        from .pipeline.utils import srgb_to_linear_lut
+        _srgb_lut_dev[key] = torch.from_numpy(srgb_to_linear_lut()).to(device)
+    return _srgb_lut_dev[key]
+
+
+def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors, poses: torch.Tensor, fx, fy, cx, cy,
+              res: int, msaa: int = 4, cull_backfaces: bool = False, uv=None, texture=None, points: bool = False):
+    """verts (V,3) fp32, faces (F,3) int32, colors (V,3) u8 | None, poses (B,4,4)|(B,3,4) fp32 -> rgb u8 (B,res,res,3),
+    depth fp32 (B,res,res).  ``texture`` = (RGBA8 mip chain u8 tensor, w, h, levels) with ``uv`` (V,2) fp32;
+    ``points`` renders the vertices as 1-pixel point sprites (faces ignored)."""
     dev = verts.device
     B = poses.shape[0]
     p34 = poses[:, :3, :4].to(torch.float32).contiguous()
     V, F = verts.shape[0], faces.shape[0]
-    assert verts.dtype == torch.float32 and faces.dtype == torch.int32 and colors.dtype == torch.uint8
+    assert verts.dtype == torch.float32 and faces.dtype == torch.int32
+    assert colors is None or colors.dtype == torch.uint8
     lib = load()
     nbytes = C.c_size_t(0)
     check(lib.fp_raster_workspace_bytes(B, V, res, msaa, C.byref(nbytes)), "fp_raster_workspace_bytes")
     ws = _ws(nbytes.value, dev)
     rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
     depth = torch.empty(B, res, res, dtype=torch.float32, device=dev)
+    chain, tw, th, tl = texture if texture is not None else (None, 0, 0, 0)
+    if texture is not None:
+        assert uv is not None and uv.dtype == torch.float32 and uv.shape == (V, 2) and chain.dtype == torch.uint8
     args = _lib.RasterArgs(ptr(verts), ptr(faces), ptr(colors), V, F, ptr(p34), B, float(fx), float(fy), float(cx),
-                           float(cy), res, msaa, int(cull_backfaces), ptr(gamma_lut(dev)), ptr(rgb), ptr(depth))
+                           float(cy), res, msaa, int(cull_backfaces), ptr(gamma_lut(dev)), ptr(rgb), ptr(depth),
+                           int(points), ptr(uv) if texture is not None else None, ptr(chain), int(tw), int(th), int(tl),
+                           ptr(srgb_lut(dev)) if texture is not None else None)
     check(lib.fp_rasterize(C.byref(args), ptr(ws), ws.numel(), stream_ptr()), "fp_rasterize")
     return rgb, depth
+
+
+def rasterize_mesh(mesh, poses: torch.Tensor, fx, fy, cx, cy, res: int, msaa: int = 4, cull_backfaces: bool = False):
+    """Any :class:`pipeline.utils.Mesh` (vertex-coloured, textured or point cloud) -> rgb, depth."""
+    from .pipeline.utils import mesh_texture_to_device, mesh_to_device
+    dev = poses.device
+    v, f, c = mesh_to_device(mesh, dev)
+    tex = mesh_texture_to_device(mesh, dev)
+    if tex is not None:
+        return rasterize(v, f, c, poses, fx, fy, cx, cy, res, msaa, cull_backfaces, uv=tex["uv"],
+                         texture=(tex["chain"], tex["w"], tex["h"], tex["levels"]))
+    return rasterize(v, f, c, poses, fx, fy, cx, cy, res, msaa, cull_backfaces, points=mesh.is_point_cloud)
 
 
 # ------------------------------------------------------------------------------------------- geometry

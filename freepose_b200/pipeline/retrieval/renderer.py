@@ -30,7 +30,6 @@ class MeshRenderer:
     def render_device(self, mesh, poses=None, cull_faces=False):
         """-> rgb u8 (B,res,res,3), depth fp32 (B,res,res) CUDA tensors."""
         m = as_mesh(mesh)
-        v, f, c = mesh_to_device(m, self.device)
         if poses is None:
             if self._poses_dev is None:
                 self._poses_dev = torch.from_numpy(np.array(self.mesh_poses)).to(self.device, torch.float32)
@@ -38,8 +37,8 @@ class MeshRenderer:
         else:
             P = torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device)
         r = self.resolution
-        return ops.rasterize(v, f, c, P, self.focal, self.focal, r / 2, r / 2, r, msaa=self.msaa,
-                             cull_backfaces=cull_faces)
+        return ops.rasterize_mesh(m, P, self.focal, self.focal, r / 2, r / 2, r, msaa=self.msaa,
+                                  cull_backfaces=cull_faces)
 
     def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None):
         """Device version of generate_proposals: mask -> bbox -> CropResizePad.  Returns

@@ -47,13 +47,22 @@ def generate_poses(n_poses: int = 600) -> list:
 
 @dataclass
 class Mesh:
-    """Minimal triangle mesh (the reference passes ``trimesh.Trimesh``; anything exposing ``vertices``,
-    ``faces`` and optionally ``visual.vertex_colors`` is accepted through :func:`as_mesh`)."""
+    """Minimal renderable (the reference passes ``trimesh.Trimesh`` / ``trimesh.PointCloud``; anything exposing
+    ``vertices`` plus ``faces`` / ``visual`` or ``colors`` is accepted through :func:`as_mesh`).
+
+    ``faces is None`` marks a point cloud (reference renderer.py:46-51).  A base-colour texture is given as ``uv``
+    (V,2, v up) + ``texture`` (H,W,3|4 u8, row 0 = top of the image, i.e. v = 1)."""
 
     vertices: np.ndarray                      # (V,3)
-    faces: np.ndarray                         # (F,3) int
+    faces: np.ndarray | None                  # (F,3) int, None = point cloud
     vertex_colors: np.ndarray | None = None   # (V,3|4) u8
+    uv: np.ndarray | None = None              # (V,2) float
+    texture: np.ndarray | None = None         # (H,W,3|4) u8
     _device_cache: dict = field(default_factory=dict, repr=False, compare=False)
+
+    @property
+    def is_point_cloud(self) -> bool:
+        return self.faces is None
 
     def apply_scale(self, s: float):
         self.vertices = np.asarray(self.vertices, dtype=np.float64) * s
@@ -61,37 +70,108 @@ class Mesh:
         return self
 
     def copy(self):
-        return Mesh(np.array(self.vertices), np.array(self.faces),
-                    None if self.vertex_colors is None else np.array(self.vertex_colors))
+        cp = lambda a: None if a is None else np.array(a)
+        return Mesh(np.array(self.vertices), cp(self.faces), cp(self.vertex_colors), cp(self.uv), cp(self.texture))
+
+
+def _texture_image(material):
+    """The base-colour image of a trimesh material (SimpleMaterial.image / PBRMaterial.baseColorTexture) as an
+    (H,W,3|4) u8 array, or None."""
+    for name in ("image", "baseColorTexture"):
+        img = getattr(material, name, None)
+        if img is None:
+            continue
+        if hasattr(img, "convert"):          # PIL image
+            img = img.convert("RGBA")
+        arr = np.asarray(img)
+        if arr.ndim == 2:
+            arr = np.repeat(arr[:, :, None], 3, axis=2)
+        if arr.ndim == 3 and arr.shape[2] in (3, 4) and arr.dtype == np.uint8:
+            return arr
+    return None
 
 
 def as_mesh(obj) -> Mesh:
+    """trimesh-like object -> :class:`Mesh`, following what ``pyrender.Mesh.from_trimesh`` / ``from_points`` read:
+    ``visual.kind == 'vertex'`` -> vertex colours, ``'texture'`` -> uv + material image, point clouds -> ``colors``
+    (white when empty, renderer.py:47-50)."""
     if isinstance(obj, Mesh):
         return obj
-    if hasattr(obj, "vertices") and hasattr(obj, "faces"):
-        colors = None
+    if hasattr(obj, "vertices") and getattr(obj, "faces", None) is not None:
+        colors = uv = tex = None
         vis = getattr(obj, "visual", None)
-        if vis is not None and getattr(vis, "kind", None) == "vertex" and getattr(vis, "vertex_colors", None) is not None:
+        kind = getattr(vis, "kind", None)
+        if kind == "vertex" and getattr(vis, "vertex_colors", None) is not None:
             colors = np.asarray(vis.vertex_colors)
-        return Mesh(np.asarray(obj.vertices), np.asarray(obj.faces), colors)
-    raise TypeError("textured meshes and point clouds are not rasterised by this build; pass a triangle mesh with "
-                    "vertices/faces (and optional per-vertex colours)")
+        elif kind == "texture" and getattr(vis, "uv", None) is not None:
+            tex = _texture_image(getattr(vis, "material", None))
+            if tex is not None:
+                uv = np.asarray(vis.uv, dtype=np.float64)
+        return Mesh(np.asarray(obj.vertices), np.asarray(obj.faces), colors, uv, tex)
+    if hasattr(obj, "vertices"):
+        colors = getattr(obj, "colors", None)
+        colors = None if colors is None or np.size(colors) == 0 else np.asarray(colors)
+        return Mesh(np.asarray(obj.vertices), None, colors)
+    raise TypeError("expected a triangle mesh (vertices/faces[/visual]) or a point cloud (vertices[/colors])")
+
+
+def build_mip_chain(image: np.ndarray):
+    """(H,W,3|4) u8 -> (flat RGBA8 bytes of every level, level 0 first; number of levels).  Each level halves both
+    sides (floor, min 1) with a 2x2 box filter in the stored (sRGB) values, rounded half up -- what glGenerateMipmap
+    does for pyrender's non-sRGB GL_RGBA textures (odd sides: the last source texel is reused)."""
+    img = np.asarray(image)
+    if img.shape[2] == 3:
+        img = np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    levels = [np.ascontiguousarray(img, dtype=np.uint8)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        src = levels[-1].astype(np.uint16)
+        H, W = src.shape[:2]
+        nh, nw = max(1, H // 2), max(1, W // 2)
+        y0, y1 = np.minimum(2 * np.arange(nh), H - 1), np.minimum(2 * np.arange(nh) + 1, H - 1)
+        x0, x1 = np.minimum(2 * np.arange(nw), W - 1), np.minimum(2 * np.arange(nw) + 1, W - 1)
+        acc = src[y0][:, x0] + src[y0][:, x1] + src[y1][:, x0] + src[y1][:, x1]
+        levels.append(((acc + 2) >> 2).astype(np.uint8))
+    return np.concatenate([l.reshape(-1) for l in levels]), len(levels)
+
+
+def srgb_to_linear_lut() -> np.ndarray:
+    """[65536] fp32 (i/65535)^2.2: pyrender's ``srgb_to_linear`` (mesh.frag), applied to the filtered texel."""
+    return np.power(np.arange(65536, dtype=np.float64) / 65535.0, 2.2).astype(np.float32)
 
 
 def mesh_to_device(mesh: Mesh, device):
-    """fp32 vertices, int32 faces, u8 RGB colours on the device (white when the mesh has no colours, which is
-    what pyrender's default material renders)."""
+    """fp32 vertices, int32 faces, u8 RGB colours on the device (white when the mesh has neither colours nor a
+    texture, which is what pyrender's default material renders; None when a texture replaces them)."""
     key = str(device)
     if key not in mesh._device_cache:
         v = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.vertices, dtype=np.float32))).to(device)
-        f = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.faces, dtype=np.int32))).to(device)
-        if mesh.vertex_colors is None:
-            c = torch.full((v.shape[0], 3), 255, dtype=torch.uint8, device=device)
+        if mesh.faces is None:
+            f = torch.zeros((0, 3), dtype=torch.int32, device=device)
         else:
+            f = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.faces, dtype=np.int32))).to(device)
+        if mesh.vertex_colors is not None:
             c = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.vertex_colors)[:, :3].astype(np.uint8))).to(device)
+        elif mesh.texture is not None and mesh.uv is not None:
+            c = None
+        else:
+            c = torch.full((v.shape[0], 3), 255, dtype=torch.uint8, device=device)
         if f.numel() and (int(f.min()) < 0 or int(f.max()) >= v.shape[0]):
             raise ValueError("mesh faces index outside the vertex array")
         mesh._device_cache[key] = (v, f, c)
+    return mesh._device_cache[key]
+
+
+def mesh_texture_to_device(mesh: Mesh, device):
+    """-> dict(uv (V,2) fp32, chain u8, w, h, levels) on the device, or None for untextured meshes."""
+    if mesh.texture is None or mesh.uv is None or mesh.faces is None:
+        return None
+    key = "tex:" + str(device)
+    if key not in mesh._device_cache:
+        chain, levels = build_mip_chain(mesh.texture)
+        mesh._device_cache[key] = dict(
+            uv=torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.uv, dtype=np.float32))).to(device),
+            chain=torch.from_numpy(chain).to(device), w=int(mesh.texture.shape[1]), h=int(mesh.texture.shape[0]),
+            levels=levels)
     return mesh._device_cache[key]
 
 

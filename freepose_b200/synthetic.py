@@ -55,6 +55,38 @@ def synthetic_mesh(seed: int = 0, subdivisions: int = 5, scale: float = 0.25) ->
     return Mesh(v * scale, f, np.clip(np.rint(col), 0, 255).astype(np.uint8))
 
 
+def synthetic_texture(seed: int = 0, width: int = 512, height: int = 256) -> np.ndarray:
+    """(H,W,3) u8: smooth colour ramps + stripes + seeded per-texel noise (the noise is what makes mip selection and
+    bilinear weights visible in the output)."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid(np.linspace(0, 1, height, endpoint=False), np.linspace(0, 1, width, endpoint=False), indexing="ij")
+    base = np.stack([0.5 + 0.5 * np.sin(2 * np.pi * (3 * u + v)), u, 0.5 + 0.5 * np.cos(2 * np.pi * 5 * v)], axis=2)
+    stripes = ((np.floor(u * 32) + np.floor(v * 16)) % 2)[:, :, None]
+    img = 0.55 * base + 0.25 * stripes + 0.2 * rng.uniform(size=(height, width, 3))
+    return np.clip(np.rint(255 * img), 0, 255).astype(np.uint8)
+
+
+def synthetic_textured_mesh(seed: int = 0, subdivisions: int = 4, tex_size=(512, 256), with_vertex_colors=False) -> Mesh:
+    """The bumpy blob of :func:`synthetic_mesh` with spherical texture coordinates (longitude, latitude of the vertex
+    direction; the seam triangles wrap around in u, which exercises REPEAT addressing and large footprints)."""
+    m = synthetic_mesh(seed, subdivisions)
+    d = m.vertices / np.linalg.norm(m.vertices, axis=1, keepdims=True)
+    uv = np.stack([0.5 + np.arctan2(d[:, 1], d[:, 0]) / (2 * np.pi), 0.5 + np.arcsin(np.clip(d[:, 2], -1, 1)) / np.pi], axis=1)
+    tex = synthetic_texture(seed, *tex_size)
+    return Mesh(m.vertices, m.faces, m.vertex_colors if with_vertex_colors else None, uv, tex)
+
+
+def synthetic_point_cloud(seed: int = 0, n: int = 20000, scale: float = 0.25) -> Mesh:
+    """Seeded coloured points on the surface of the blob (a stand-in for reconstructed point-cloud models)."""
+    rng = np.random.default_rng(seed)
+    m = synthetic_mesh(seed, 4, scale)
+    tri = m.vertices[m.faces[rng.integers(0, len(m.faces), size=n)]]
+    w = rng.dirichlet(np.ones(3), size=n)
+    pts = (tri * w[:, :, None]).sum(1)
+    col = np.clip(np.rint(60 + 60 * (1 + np.sin(20 * pts @ rng.normal(size=(3, 3))))), 0, 255).astype(np.uint8)
+    return Mesh(pts, None, col)
+
+
 def camera_for(resolution: int):
     """Reference template camera K = [[600,0,210],[0,600,210],[0,0,1]] at 420 px (renderer.py:37,
     template.py:96), scaled with the resolution so the object fills the same image fraction."""

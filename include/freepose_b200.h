@@ -30,7 +30,7 @@ extern "C" {
 #define FP_API
 #endif
 
-#define FP_ABI_VERSION 1
+#define FP_ABI_VERSION 2
 
 FP_API int fp_abi_version(void);
 FP_API const char* fp_last_error(void);
@@ -174,6 +174,14 @@ typedef struct fp_raster_args {
   const uint8_t* gamma_lut; /* [65536] u8: round(255 * (i/65535)^(1/2.2))                                */
   uint8_t* rgb;             /* out [B,res,res,3] u8                                                      */
   float* depth;             /* out [B,res,res] fp32 metres, 0 = background                               */
+  /* ABI 2: the other two inputs renderer.py:43-51,70-78 accepts */
+  int primitive;            /* 0 = triangles; 1 = points (trimesh.PointCloud -> pyrender.Mesh.from_points: one
+                               1-pixel sprite per vertex, flat vertex colour; faces/F ignored)                */
+  const float* uv;          /* [V,2] fp32 texture coordinates, v up (trimesh TextureVisuals.uv), or NULL    */
+  const uint8_t* texture;   /* RGBA8 mip chain (level 0 first; level l is max(1,w>>l) x max(1,h>>l), rows
+                               top-down), or NULL = vertex colours only; colors may be NULL with a texture   */
+  int tex_w, tex_h, tex_levels;
+  const float* srgb_lut;    /* [65536] fp32: (i/65535)^2.2, pyrender's srgb_to_linear applied after filtering */
 } fp_raster_args;
 FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes /* host out */);
 FP_API int fp_rasterize(const fp_raster_args* args /* host struct */, void* workspace, size_t workspace_bytes,

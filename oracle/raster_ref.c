@@ -2,6 +2,8 @@
  * reference obtains from pyrender/OpenGL (reference src/pipeline/retrieval/renderer.py:37-66): pinhole camera
  * in the OpenCV frame, two-sided triangles, ambient-only (2,2,2) lighting with 1/2.2 gamma, transparent black
  * background, 4x multisampling with one shading sample per (triangle, pixel), linear depth of sample 0.
+ * Surfaces: vertex colours, a base-colour texture (REPEAT wrap, trilinear over the caller's box-filtered mip chain,
+ * x^2.2 after filtering, optional vertex-colour multiplier) or 1-pixel point sprites (trimesh.PointCloud inputs).
  *
  * pyrender / PyOpenGL / EGL are not installed and OpenGL rasterisation is not bit-specified, so this oracle
  * cannot be pinned against the real renderer: PARITY UNPINNED for row R.  What it pins is that the
@@ -44,16 +46,138 @@ static void project(const float* verts, const float* P, int V, float fx, float f
 static int imin(int a, int b) { return a < b ? a : b; }
 static int imax(int a, int b) { return a > b ? a : b; }
 
+typedef struct {
+  const uint8_t* colors;    /* [V,3] or NULL */
+  const float* uv;          /* [V,2] or NULL */
+  const uint8_t* texture;   /* RGBA8 mip chain or NULL */
+  const float* srgb_lut;    /* [65536] */
+  const uint8_t* gamma_lut; /* [65536] */
+  int tex_w, tex_h, tex_levels;
+  int points;
+} Surface;
+
+static int to_unorm8(float lin, const uint8_t* lut) {
+  lin = fminf(fmaxf(lin, 0.f), 1.f);
+  if (!(lin == lin)) lin = 0.f;
+  return lut[(int)(lin * 65535.0f + 0.5f)];
+}
+
+static int wrap_repeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+
+static void bilinear(const Surface* sf, int lvl, float u, float v, float out[3]) {
+  size_t off = 0;
+  int W = sf->tex_w, H = sf->tex_h;
+  for (int l = 0; l < lvl; ++l) { off += (size_t)W * H * 4; W = imax(1, W >> 1); H = imax(1, H >> 1); }
+  float x = u * (float)W + -0.5f;
+  float y = (1.0f + -v) * (float)H + -0.5f;
+  float xf = floorf(x), yf = floorf(y);
+  float fx = x + -xf, fy = y + -yf;
+  int ix = (int)fminf(fmaxf(xf, -1.0e9f), 1.0e9f), iy = (int)fminf(fmaxf(yf, -1.0e9f), 1.0e9f);
+  int x0 = wrap_repeat(ix, W), x1 = wrap_repeat(ix + 1, W), y0 = wrap_repeat(iy, H), y1 = wrap_repeat(iy + 1, H);
+  const uint8_t* t = sf->texture + off;
+  for (int ch = 0; ch < 3; ++ch) {
+    float a00 = (float)t[((size_t)y0 * W + x0) * 4 + ch], a10 = (float)t[((size_t)y0 * W + x1) * 4 + ch];
+    float a01 = (float)t[((size_t)y1 * W + x0) * 4 + ch], a11 = (float)t[((size_t)y1 * W + x1) * 4 + ch];
+    float top = a00 + fx * (a10 + -a00);
+    float bot = a01 + fx * (a11 + -a01);
+    out[ch] = top + fy * (bot + -top);
+  }
+}
+
+static float lod_from_rho2(float rho2, int levels) {
+  float top = (float)(levels - 1);
+  if (!(rho2 < 1.0e30f)) return top;
+  if (!(rho2 > 1.0f)) return 0.f;
+  uint32_t bits;
+  memcpy(&bits, &rho2, 4);
+  float e = (float)((int)(bits >> 23) - 127);
+  float m = (float)(bits & 0x7fffffu) * 1.1920928955078125e-07f;
+  return fminf(0.5f * (e + m), top);
+}
+
+typedef struct { float w0, w1, w2, wsum; } Weights;
+
+static Weights persp_weights(SV v0, SV v1, SV v2, float fa, int64_t sx, int64_t sy) {
+  int64_t e0 = (int64_t)(v2.x - v1.x) * (sy - v1.y) - (int64_t)(v2.y - v1.y) * (sx - v1.x);
+  int64_t e1 = (int64_t)(v0.x - v2.x) * (sy - v2.y) - (int64_t)(v0.y - v2.y) * (sx - v2.x);
+  int64_t e2 = (int64_t)(v1.x - v0.x) * (sy - v0.y) - (int64_t)(v1.y - v0.y) * (sx - v0.x);
+  Weights w;
+  w.w0 = ((float)e0 / fa) * v0.iz; w.w1 = ((float)e1 / fa) * v1.iz; w.w2 = ((float)e2 / fa) * v2.iz;
+  w.wsum = (w.w0 + w.w1) + w.w2;
+  return w;
+}
+static float interp(Weights w, float a0, float a1, float a2) { return ((w.w0 * a0 + w.w1 * a1) + w.w2 * a2) / w.wsum; }
+
+/* colour of triangle f at the centre of pixel (px, py) -> out[3] unorm8 */
+static void shade(const Surface* sf, const int32_t* faces, const SV* sv, int f, int px, int py, int out[3]) {
+  int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+  SV v0 = sv[i0], v1 = sv[i1], v2 = sv[i2];
+  int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
+  if (area < 0) { SV t = v1; v1 = v2; v2 = t; int ti = i1; i1 = i2; i2 = ti; area = -area; }
+  float fa = (float)area;
+  int64_t sx = ((int64_t)px << SUB) + 128, sy = ((int64_t)py << SUB) + 128;
+  Weights w = persp_weights(v0, v1, v2, fa, sx, sy);
+  float vc[3] = {255.f, 255.f, 255.f};
+  if (sf->texture == NULL || sf->colors != NULL)
+    for (int ch = 0; ch < 3; ++ch)
+      vc[ch] = interp(w, (float)sf->colors[3 * i0 + ch], (float)sf->colors[3 * i1 + ch], (float)sf->colors[3 * i2 + ch]);
+  if (sf->texture == NULL) {
+    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(vc[ch] * (2.0f / 255.0f), sf->gamma_lut);
+    return;
+  }
+  float ua = sf->uv[2 * i0], ub = sf->uv[2 * i1], uc = sf->uv[2 * i2];
+  float va = sf->uv[2 * i0 + 1], vb = sf->uv[2 * i1 + 1], vcc = sf->uv[2 * i2 + 1];
+  float u = interp(w, ua, ub, uc), v = interp(w, va, vb, vcc);
+  Weights wx = persp_weights(v0, v1, v2, fa, sx + ONE, sy), wy = persp_weights(v0, v1, v2, fa, sx, sy + ONE);
+  float fw = (float)sf->tex_w, fh = (float)sf->tex_h;
+  float dux = (interp(wx, ua, ub, uc) + -u) * fw, dvx = (interp(wx, va, vb, vcc) + -v) * fh;
+  float duy = (interp(wy, ua, ub, uc) + -u) * fw, dvy = (interp(wy, va, vb, vcc) + -v) * fh;
+  float rx = dux * dux + dvx * dvx, ry = duy * duy + dvy * dvy;
+  float lod = lod_from_rho2(fmaxf(rx, ry), sf->tex_levels);
+  int l0 = (int)lod;
+  float t = lod + -(float)l0;
+  float ca[3];
+  bilinear(sf, l0, u, v, ca);
+  if (t > 0.f) {
+    float cb[3];
+    bilinear(sf, imin(l0 + 1, sf->tex_levels - 1), u, v, cb);
+    for (int ch = 0; ch < 3; ++ch) ca[ch] = ca[ch] + t * (cb[ch] + -ca[ch]);
+  }
+  for (int ch = 0; ch < 3; ++ch) {
+    float cn = ca[ch] / 255.0f;
+    cn = fminf(fmaxf(cn, 0.f), 1.f);
+    if (!(cn == cn)) cn = 0.f;
+    float lin = sf->srgb_lut[(int)(cn * 65535.0f + 0.5f)];
+    if (sf->colors != NULL) lin = lin * (vc[ch] / 255.0f);
+    out[ch] = to_unorm8(lin * 2.0f, sf->gamma_lut);
+  }
+}
+
 /* One view.  rgb: res*res*3 u8, depth: res*res f32. */
-static void render_view(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F,
+static void render_view(const float* verts, const int32_t* faces, const Surface* sf, int V, int F,
                         const float* P, float fx, float fy, float cx, float cy, int res, int msaa, int cull,
-                        const uint8_t* lut, uint8_t* rgb, float* depth, SV* sv, float* zbuf, int32_t* fbuf) {
+                        uint8_t* rgb, float* depth, SV* sv, float* zbuf, int32_t* fbuf) {
   const int S = msaa;
   const int (*off)[2] = (S == 4) ? OFF4 : OFF1;
   project(verts, P, V, fx, fy, cx, cy, sv);
   const size_t ns = (size_t)res * res * S;
   for (size_t i = 0; i < ns; ++i) { zbuf[i] = INFINITY; fbuf[i] = -1; }
-  for (int f = 0; f < F; ++f) {
+  /* GL_POINTS, size 1: square sprite [x-.5, x+.5) x [y-.5, y+.5), flat depth; lower vertex index wins depth ties */
+  for (int i = 0; sf->points && i < V; ++i) {
+    if (!sv[i].ok || !(sv[i].z > ZNEAR && sv[i].z < ZFAR)) continue;
+    int bx = sv[i].x - ONE / 2, by = sv[i].y - ONE / 2;
+    for (int py = by >> SUB; py <= (by + ONE - 1) >> SUB; ++py)
+      for (int px = bx >> SUB; px <= (bx + ONE - 1) >> SUB; ++px) {
+        if (px < 0 || px >= res || py < 0 || py >= res) continue;
+        for (int s = 0; s < S; ++s) {
+          int sx = (px << SUB) + off[s][0], sy = (py << SUB) + off[s][1];
+          if (sx < bx || sx >= bx + ONE || sy < by || sy >= by + ONE) continue;
+          size_t k = ((size_t)py * res + px) * S + s;
+          if (sv[i].z < zbuf[k]) { zbuf[k] = sv[i].z; fbuf[k] = i; }
+        }
+      }
+  }
+  for (int f = 0; !sf->points && f < F; ++f) {
     SV v0 = sv[faces[3 * f]], v1 = sv[faces[3 * f + 1]], v2 = sv[faces[3 * f + 2]];
     if (!v0.ok || !v1.ok || !v2.ok) continue;
     int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
@@ -98,26 +222,12 @@ static void render_view(const float* verts, const int32_t* faces, const uint8_t*
       for (int s = 0; s < S; ++s) {
         int f = fbuf[k0 + s];
         if (f < 0) continue;
-        int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-        SV v0 = sv[i0], v1 = sv[i1], v2 = sv[i2];
-        int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
-        if (area < 0) { SV t = v1; v1 = v2; v2 = t; int ti = i1; i1 = i2; i2 = ti; area = -area; }
-        int64_t sx = ((int64_t)px << SUB) + 128, sy = ((int64_t)py << SUB) + 128;
-        int64_t e0 = (int64_t)(v2.x - v1.x) * (sy - v1.y) - (int64_t)(v2.y - v1.y) * (sx - v1.x);
-        int64_t e1 = (int64_t)(v0.x - v2.x) * (sy - v2.y) - (int64_t)(v0.y - v2.y) * (sx - v2.x);
-        int64_t e2 = (int64_t)(v1.x - v0.x) * (sy - v0.y) - (int64_t)(v1.y - v0.y) * (sx - v0.x);
-        float fa = (float)area;
-        float w0 = ((float)e0 / fa) * v0.iz, w1 = ((float)e1 / fa) * v1.iz, w2 = ((float)e2 / fa) * v2.iz;
-        float wsum = (w0 + w1) + w2;
-        for (int ch = 0; ch < 3; ++ch) {
-          float a0 = (float)colors[3 * i0 + ch], a1 = (float)colors[3 * i1 + ch], a2 = (float)colors[3 * i2 + ch];
-          float c = ((w0 * a0 + w1 * a1) + w2 * a2) / wsum;
-          float lin = c * (2.0f / 255.0f);
-          lin = fminf(fmaxf(lin, 0.f), 1.f);
-          if (!(lin == lin)) lin = 0.f;
-          int idx = (int)(lin * 65535.0f + 0.5f);
-          acc[ch] += lut[idx];
-        }
+        int col[3];
+        if (sf->points)
+          for (int ch = 0; ch < 3; ++ch) col[ch] = to_unorm8((float)sf->colors[3 * f + ch] * (2.0f / 255.0f), sf->gamma_lut);
+        else
+          shade(sf, faces, sv, f, px, py, col);
+        for (int ch = 0; ch < 3; ++ch) acc[ch] += col[ch];
       }
       uint8_t* o = rgb + ((size_t)py * res + px) * 3;
       for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)(S == 4 ? (acc[ch] + 2) >> 2 : acc[ch]);
@@ -125,17 +235,27 @@ static void render_view(const float* verts, const int32_t* faces, const uint8_t*
     }
 }
 
-int raster_ref(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
-               int B, float fx, float fy, float cx, float cy, int res, int msaa, int cull, const uint8_t* lut,
-               uint8_t* rgb, float* depth) {
+int raster_ref2(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
+                int B, float fx, float fy, float cx, float cy, int res, int msaa, int cull, const uint8_t* lut,
+                uint8_t* rgb, float* depth, int points, const float* uv, const uint8_t* texture, int tex_w, int tex_h,
+                int tex_levels, const float* srgb_lut) {
   if (msaa != 1 && msaa != 4) return -1;
+  if (texture == NULL && colors == NULL) return -3;
+  Surface sf = {colors, uv, texture, srgb_lut, lut, tex_w, tex_h, tex_levels, points};
   SV* sv = (SV*)malloc(sizeof(SV) * (size_t)V);
   float* zbuf = (float*)malloc(sizeof(float) * (size_t)res * res * msaa);
   int32_t* fbuf = (int32_t*)malloc(sizeof(int32_t) * (size_t)res * res * msaa);
   if (!sv || !zbuf || !fbuf) return -2;
   for (int b = 0; b < B; ++b)
-    render_view(verts, faces, colors, V, F, poses + (size_t)b * 12, fx, fy, cx, cy, res, msaa, cull, lut,
+    render_view(verts, faces, &sf, V, F, poses + (size_t)b * 12, fx, fy, cx, cy, res, msaa, cull,
                 rgb + (size_t)b * res * res * 3, depth + (size_t)b * res * res, sv, zbuf, fbuf);
   free(sv); free(zbuf); free(fbuf);
   return 0;
+}
+
+int raster_ref(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
+               int B, float fx, float fy, float cx, float cy, int res, int msaa, int cull, const uint8_t* lut,
+               uint8_t* rgb, float* depth) {
+  return raster_ref2(verts, faces, colors, V, F, poses, B, fx, fy, cx, cy, res, msaa, cull, lut, rgb, depth, 0, NULL,
+                     NULL, 0, 0, 0, NULL);
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
-    assert lib.fp_abi_version() == 1
+    assert lib.fp_abi_version() == 2
     # no torch / C++ types leak through the boundary: only the declared C symbols are default-visible
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}

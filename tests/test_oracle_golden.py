@@ -191,3 +191,43 @@ def test_numpy_order_mean_is_numpy_mean():
         for _ in range(10):
             v = rng.standard_normal(n).astype(np.float32)
             assert numpy_order_mean(v) == v.mean()
+
+
+# ------------------------------------------------------------------------------------------- raster oracle: surfaces
+def test_raster_oracle_uniform_texture_matches_closed_form():
+    """A constant texture must come out as gamma(2 * (c/255)^2.2) wherever the mesh is hit (pyrender: srgb_to_linear on
+    the texel, ambient (2,2,2), 1/2.2 gamma), for every mip level and filter weight."""
+    from freepose_b200.pipeline.utils import Mesh, generate_poses
+    from freepose_b200.synthetic import synthetic_textured_mesh
+    from oracle import raster as R
+    m = synthetic_textured_mesh(0, 2)
+    poses = np.array(generate_poses(3))
+    for c in (0, 37, 100, 180, 255):
+        tex = np.full((16, 32, 3), c, np.uint8)
+        rgb, depth = R.render_mesh(Mesh(m.vertices, m.faces, None, m.uv, tex), poses, 320, 320, 112, 112, 224, msaa=1)
+        want = int(np.floor(255 * min(1.0, 2 * (c / 255) ** 2.2) ** (1 / 2.2) + 0.5))
+        got = np.unique(rgb[depth > 0])
+        assert len(got) == 1 and abs(int(got[0]) - want) <= 1, (c, got, want)
+
+
+def test_mip_chain_and_trimesh_adapters():
+    from types import SimpleNamespace as NS
+    from freepose_b200.pipeline.utils import as_mesh, build_mip_chain
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(5, 12, 3), dtype=np.uint8)
+    chain, levels = build_mip_chain(img)
+    sizes = [(12, 5), (6, 2), (3, 1), (1, 1)]
+    assert levels == len(sizes) and chain.size == sum(w * h * 4 for w, h in sizes)
+    l1 = chain[12 * 5 * 4:12 * 5 * 4 + 6 * 2 * 4].reshape(2, 6, 4)
+    want = (img[0:2, 0:2].astype(int).sum((0, 1)) + 2) >> 2
+    assert np.array_equal(l1[0, 0, :3], want) and l1[0, 0, 3] == 255
+    tri = NS(vertices=np.zeros((3, 3)), faces=np.array([[0, 1, 2]]),
+             visual=NS(kind="texture", uv=np.zeros((3, 2)), material=NS(image=img)))
+    m = as_mesh(tri)
+    assert m.texture is img or np.array_equal(m.texture, img)
+    assert m.uv.shape == (3, 2) and not m.is_point_cloud
+    pc = as_mesh(NS(vertices=np.zeros((4, 3)), colors=np.zeros((0, 4))))
+    assert pc.is_point_cloud and pc.vertex_colors is None
+    vc = as_mesh(NS(vertices=np.zeros((3, 3)), faces=np.array([[0, 1, 2]]),
+                    visual=NS(kind="vertex", vertex_colors=np.full((3, 4), 9, np.uint8))))
+    assert vc.vertex_colors.shape == (3, 4) and vc.texture is None
