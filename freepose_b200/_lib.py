@@ -29,7 +29,8 @@ class VitLayer(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [("depth", C.c_int), ("layers", C.POINTER(VitLayer)), ("patch_w", C.c_void_p),
                 ("patch_b", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p),
-                ("pos_res", C.c_int), ("pos_embed", C.c_void_p), ("special_tokens", C.c_void_p)]
+                ("pos_res", C.c_int), ("pos_embed", C.c_void_p), ("special_tokens", C.c_void_p),
+                ("dim", C.c_int), ("heads", C.c_int), ("mlp_dim", C.c_int)]
 
 
 class RasterArgs(C.Structure):
@@ -38,7 +39,8 @@ class RasterArgs(C.Structure):
                 ("cx", C.c_float), ("cy", C.c_float), ("res", C.c_int), ("msaa", C.c_int),
                 ("cull_backfaces", C.c_int), ("gamma_lut", C.c_void_p), ("rgb", C.c_void_p),
                 ("depth", C.c_void_p), ("primitive", C.c_int), ("uv", C.c_void_p), ("texture", C.c_void_p),
-                ("tex_w", C.c_int), ("tex_h", C.c_int), ("tex_levels", C.c_int), ("srgb_lut", C.c_void_p)]
+                ("tex_w", C.c_int), ("tex_h", C.c_int), ("tex_levels", C.c_int), ("srgb_lut", C.c_void_p),
+                ("ambient", C.c_float), ("znear", C.c_float), ("zfar", C.c_float), ("view_k", C.c_void_p)]
 
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -54,10 +56,10 @@ SIGNATURES = {
     "fp_profile_num_kinds": (_i, []),
     "fp_profile_kind_name": (C.c_char_p, [_i]),
     "fp_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
-    "fp_vit_workspace_bytes": (_sz, [_i, _i]),
+    "fp_vit_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "fp_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "fp_gemm_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "fp_layernorm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
+    "fp_layernorm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp]),
     "fp_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     "fp_im2col_patches": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "fp_normalize_image": (_i, [_vp, _vp, _i, _i, _vp]),

@@ -25,7 +25,9 @@ FP_API int fp_profile_collect(int kind, double* total_ms, double* total_work, lo
   return fp::prof_collect(kind, total_ms, total_work, launches);
 }
 
-FP_API size_t fp_vit_workspace_bytes(int batch, int res) { return fp::vit_workspace_bytes(batch, res); }
+FP_API size_t fp_vit_workspace_bytes(int dim, int mlp_dim, int batch, int res) {
+  return fp::vit_workspace_bytes(dim, mlp_dim, batch, res);
+}
 
 FP_API int fp_vit_forward(const fp_vit_weights* weights, const void* input, int input_kind, int batch, int res,
                           int layer, int feature_type, void* out_tokens_bf16, void* workspace,
@@ -45,9 +47,9 @@ FP_API int fp_gemm_bf16(const void* A, int lda, const void* W, void* out, int ld
   return fp::gemm_bf16(a, S(stream));
 }
 
-FP_API int fp_layernorm_bf16(const void* x, const void* w, const void* b, void* out, int rows, float eps,
+FP_API int fp_layernorm_bf16(const void* x, const void* w, const void* b, void* out, int rows, int dim, float eps,
                              int in_group_stride, int in_skip, int rows_per_group, void* stream) {
-  return fp::layernorm_bf16(B16(x), B16(w), B16(b), B16(out), rows, 1024, eps, in_group_stride, in_skip,
+  return fp::layernorm_bf16(B16(x), B16(w), B16(b), B16(out), rows, dim, eps, in_group_stride, in_skip,
                             rows_per_group, S(stream));
 }
 
@@ -133,6 +135,7 @@ FP_API int fp_rasterize(const fp_raster_args* g, void* workspace, size_t workspa
   a.rgb = g->rgb; a.depth = g->depth;
   a.primitive = g->primitive; a.uv = g->uv; a.texture = g->texture;
   a.tex_w = g->tex_w; a.tex_h = g->tex_h; a.tex_levels = g->tex_levels; a.srgb_lut = g->srgb_lut;
+  a.ambient = g->ambient; a.znear = g->znear; a.zfar = g->zfar; a.view_k = g->view_k;
   return fp::rasterize(a, workspace, workspace_bytes, S(stream));
 }
 

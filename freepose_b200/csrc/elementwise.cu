@@ -8,16 +8,17 @@ namespace fp {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over rows of D = 1024 (one warp per row, 4 x 16-byte loads per lane, fp32 two-pass stats).
-// Contract (oracle/vit.py contract_layernorm): y = bf16(((x - mean) * rstd) * w + b).
+// LayerNorm over rows of D = 256 * NCH (ViT-L: 1024, ViT-B: 768): one warp per row, NCH x 16-byte loads per lane,
+// fp32 two-pass stats.  Contract (oracle/vit.py contract_layernorm): y = bf16(((x - mean) * rstd) * w + b).
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_D = 1024;
 constexpr int LN_WARPS = 8;
 
+template <int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
                  bf16* __restrict__ out, int rows, float eps, int in_group_stride, int in_skip,
                  int rows_per_group) {
+  constexpr int LN_D = NCH * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * LN_WARPS + warp;
   if (r >= rows) return;
@@ -25,9 +26,9 @@ layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const b
   const int idx = r - grp * rows_per_group;
   const size_t in_row = size_t(grp) * in_group_stride + in_skip + idx;
   const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * LN_D);
-  float v[32];
+  float v[NCH * 8];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const uint4 u = xp[c * 32 + lane];
     const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -38,11 +39,11 @@ layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const b
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
+  for (int i = 0; i < NCH * 8; ++i) s += v[i];
   const float mean = warp_sum(s) * (1.0f / LN_D);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < NCH * 8; ++i) {
     v[i] -= mean;
     ss = fmaf(v[i], v[i], ss);
   }
@@ -51,7 +52,7 @@ layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const b
   const uint4* bp = reinterpret_cast<const uint4*>(b);
   uint4* op = reinterpret_cast<uint4*>(out + size_t(r) * LN_D);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const uint4 wu = __ldg(wp + c * 32 + lane), bu = __ldg(bp + c * 32 + lane);
     const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
     const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
@@ -129,13 +130,17 @@ special_tokens_kernel(const bf16* __restrict__ special, bf16* __restrict__ token
 
 int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int rows, int D, float eps,
                    int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream) {
-  FP_REQUIRE(D == LN_D, "layernorm: D=%d unsupported (this path is ViT-L, D=1024)", D);
+  FP_REQUIRE(D == 1024 || D == 768, "layernorm: D=%d unsupported (ViT-L: 1024, ViT-B: 768)", D);
   if (rows <= 0) return 0;
   FP_REQUIRE(rows_per_group > 0, "layernorm: rows_per_group must be positive");
   const int blocks = (rows + LN_WARPS - 1) / LN_WARPS;
   ProfScope prof(PROF_LAYERNORM, 2.0 * double(rows) * D * 2, 1, stream);
-  layernorm_kernel<<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
-                                                         rows_per_group);
+  if (D == 1024)
+    layernorm_kernel<4><<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
+                                                              rows_per_group);
+  else
+    layernorm_kernel<3><<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
+                                                              rows_per_group);
   FP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -108,6 +108,9 @@ struct RasterArgs {
   const uint8_t* texture; // RGBA8 mip chain or null
   int tex_w, tex_h, tex_levels;
   const float* srgb_lut;  // [65536] fp32
+  float ambient;          // 0 = 2.0
+  float znear, zfar;      // 0 = 0.05 / 100
+  const float* view_k;    // [B, 4] per-view fx, fy, cx, cy or null
 };
 int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes);
 int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -126,7 +129,7 @@ int depth_extents(const float* depth, const int32_t* view_idx, int n_out, int re
 // ---------------------------------------------------------------------------------------- ViT
 struct fp_vit_weights;
 namespace fp {
-size_t vit_workspace_bytes(int B, int res);
+size_t vit_workspace_bytes(int dim, int mlp_dim, int B, int res);
 int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int B, int res, int layer,
                 int feature_type, void* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace fp

@@ -32,8 +32,8 @@ namespace {
 
 constexpr int SUB = 8;                 // sub-pixel bits
 constexpr int ONE = 1 << SUB;          // 256
-constexpr float ZNEAR = 0.05f;         // pyrender IntrinsicsCamera default
-constexpr float ZFAR = 100.0f;
+constexpr float ZNEAR_DEFAULT = 0.05f;   // pyrender IntrinsicsCamera defaults (renderer.py:37)
+constexpr float ZFAR_DEFAULT = 100.0f;
 constexpr int COORD_LIMIT = 1 << 22;   // |fixed-point coordinate| guard (16384 px)
 
 struct __align__(16) ScreenVertex {
@@ -55,10 +55,14 @@ clear_keys_kernel(unsigned long long* __restrict__ keys, size_t n) {
 
 __global__ void __launch_bounds__(256)
 vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, ScreenVertex* __restrict__ sv,
-              int V, int B, float fx, float fy, float cx, float cy) {
+              int V, int B, float fx, float fy, float cx, float cy, const float* __restrict__ view_k, float ZNEAR,
+              float ZFAR) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= V) return;
+  if (view_k != nullptr) {   // per-view intrinsics (the refiner renders every frame at its own cropped K)
+    fx = view_k[4 * b]; fy = view_k[4 * b + 1]; cx = view_k[4 * b + 2]; cy = view_k[4 * b + 3];
+  }
   const float* P = poses + size_t(b) * 12;
   const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
   // cam = R * v + t, evaluated as ((r0*x + r1*y) + r2*z) + t
@@ -138,7 +142,8 @@ __device__ __forceinline__ float sample_depth(const TriSetup& t, long long e0, l
 
 template <int S>
 __device__ __forceinline__ void raster_pixel(const TriSetup& t, const long long* bias, int px, int py,
-                                             unsigned long long* __restrict__ keys_view, int res, unsigned face) {
+                                             unsigned long long* __restrict__ keys_view, int res, unsigned face,
+                                             float ZNEAR, float ZFAR) {
   const long long bx = (long long)px << SUB, by = (long long)py << SUB;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
@@ -161,7 +166,7 @@ constexpr int BIG_TRI_PIXELS = 64;
 template <int S>
 __global__ void __launch_bounds__(256)
 triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ faces,
-                unsigned long long* __restrict__ keys, int V, int F, int res, int cull) {
+                unsigned long long* __restrict__ keys, int V, int F, int res, int cull, float ZNEAR, float ZFAR) {
   const int b = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -185,7 +190,7 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   const bool big = w * h > BIG_TRI_PIXELS;
   if (t.valid && !big) {
     for (int py = t.ymin; py <= t.ymax; ++py)
-      for (int px = t.xmin; px <= t.xmax; ++px) raster_pixel<S>(t, bias, px, py, keys_view, res, unsigned(f));
+      for (int px = t.xmin; px <= t.xmax; ++px) raster_pixel<S>(t, bias, px, py, keys_view, res, unsigned(f), ZNEAR, ZFAR);
   }
   // large triangles: the whole warp walks the bounding box of one triangle at a time
   unsigned todo = __ballot_sync(0xffffffffu, big);
@@ -211,7 +216,7 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
     const unsigned uf = unsigned(__shfl_sync(0xffffffffu, f, src));
     for (int i = lane; i < uw * uh; i += 32) {
       const int py = u.ymin + i / uw, px = u.xmin + i % uw;
-      raster_pixel<S>(u, ub, px, py, keys_view, res, uf);
+      raster_pixel<S>(u, ub, px, py, keys_view, res, uf, ZNEAR, ZFAR);
     }
   }
 }
@@ -220,7 +225,8 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
 // around the projected vertex; every sample inside it takes the vertex depth.  Key payload = vertex index.
 template <int S>
 __global__ void __launch_bounds__(256)
-point_kernel(const ScreenVertex* __restrict__ sv, unsigned long long* __restrict__ keys, int V, int res) {
+point_kernel(const ScreenVertex* __restrict__ sv, unsigned long long* __restrict__ keys, int V, int res, float ZNEAR,
+             float ZFAR) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
@@ -253,6 +259,8 @@ struct Surface {
   const float* srgb_lut;    // [65536] (i/65535)^2.2
   const uint8_t* gamma_lut; // [65536]
   int tex_w, tex_h, tex_levels;
+  float ambient;            // scene ambient light (2 in renderer.py:53-55, 5 in tracking_refiner.py:34)
+  float ambient_255;        // ambient / 255
 };
 
 // linear colour (already x ambient) -> unorm8 through the gamma LUT
@@ -345,9 +353,9 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
                       float(sf.colors[3 * c2 + ch]));
   }
   if (MODE == 0) {
-    // base colour in [0,1] is c/255; ambient (2,2,2): linear = 2c/255, clamped; LUT index = round(linear*65535)
+    // base colour in [0,1] is c/255; ambient (a,a,a): linear = a*c/255, clamped; LUT index = round(linear*65535)
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(__fmul_rn(vc[ch], 2.0f / 255.0f), sf.gamma_lut);
+    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(__fmul_rn(vc[ch], sf.ambient_255), sf.gamma_lut);
     return;
   }
   const float ua = sf.uv[2 * c0], ub = sf.uv[2 * c1], uc = sf.uv[2 * c2];
@@ -382,7 +390,7 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
     if (!(cn == cn)) cn = 0.f;
     float lin = sf.srgb_lut[int(__fadd_rn(__fmul_rn(cn, 65535.0f), 0.5f))];           // sRGB -> linear after filtering
     if (sf.colors != nullptr) lin = __fmul_rn(lin, __fdiv_rn(vc[ch], 255.0f));         // COLOR_0 multiplier
-    out[ch] = to_unorm8(__fmul_rn(lin, 2.0f), sf.gamma_lut);
+    out[ch] = to_unorm8(__fmul_rn(lin, sf.ambient), sf.gamma_lut);
   }
 }
 
@@ -417,7 +425,7 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
           if (MODE == 2) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
-              col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), 2.0f / 255.0f), sf.gamma_lut);
+              col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), sf.ambient_255), sf.gamma_lut);
           } else {
             shade<MODE>(svb, faces, sf, face, px0 + i, py, col);
           }
@@ -446,18 +454,21 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int S>
-int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* keys, cudaStream_t stream) {
+int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* keys, float znear, float zfar,
+                  cudaStream_t stream) {
   Surface sf;
+  sf.ambient = a.ambient > 0.f ? a.ambient : 2.0f;
+  sf.ambient_255 = sf.ambient / 255.0f;
   sf.colors = a.colors; sf.uv = a.uv; sf.texture = a.texture; sf.srgb_lut = a.srgb_lut; sf.gamma_lut = a.gamma_lut;
   sf.tex_w = a.tex_w; sf.tex_h = a.tex_h; sf.tex_levels = a.tex_levels;
   const dim3 rgrid((a.res * a.res / 4 + 255) / 256, a.B);
   if (a.primitive == 1) {
-    point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res);
+    point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res, znear, zfar);
     FP_CUDA(cudaGetLastError());
     resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
   } else {
     triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res,
-                                                                         a.cull_backfaces);
+                                                                         a.cull_backfaces, znear, zfar);
     FP_CUDA(cudaGetLastError());
     if (a.texture != nullptr)
       resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
@@ -502,9 +513,11 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
   ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, 4, stream);  // algorithmic bytes: RGB u8 + depth f32 out
   clear_keys_kernel<<<sm_count() * 8, 256, 0, stream>>>(keys, nkeys);
   FP_CUDA(cudaGetLastError());
-  vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy);
+  const float znear = a.znear > 0.f ? a.znear : ZNEAR_DEFAULT, zfar = a.zfar > 0.f ? a.zfar : ZFAR_DEFAULT;
+  vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy,
+                                                                  a.view_k, znear, zfar);
   FP_CUDA(cudaGetLastError());
-  return a.msaa == 4 ? launch_raster<4>(a, sv, keys, stream) : launch_raster<1>(a, sv, keys, stream);
+  return a.msaa == 4 ? launch_raster<4>(a, sv, keys, znear, zfar, stream) : launch_raster<1>(a, sv, keys, znear, zfar, stream);
 }
 
 }  // namespace fp

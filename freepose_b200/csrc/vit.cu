@@ -1,4 +1,4 @@
-// DINOv2 ViT-L/14-reg forward to layer L + final norm (reference src/pipeline/retrieval/dino.py:14-32):
+// DINOv2 ViT-L/14-reg (or ViT-B/14-reg: dim 768, 12 heads, MLP 3072) forward to layer L + final norm (reference src/pipeline/retrieval/dino.py:14-32):
 // sequencing of the kernels over caller-provided workspace.  Stateless: weights and buffers are borrowed
 // device pointers (include/freepose_b200.h: fp_vit_weights / fp_vit_forward).
 #include "common.cuh"
@@ -8,11 +8,12 @@
 namespace fp {
 
 namespace {
-constexpr int D = 1024, HEADS = 16, MLP = 4096, KPAD = 640, NREG = 4;
+constexpr int KPAD = 640, NREG = 4;
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 }  // namespace
 
-size_t vit_workspace_bytes(int B, int res) {
+size_t vit_workspace_bytes(int dim, int mlp_dim, int B, int res) {
+  const size_t D = dim > 0 ? dim : 1024, MLP = mlp_dim > 0 ? mlp_dim : 4096;
   const int g = res / 14, P = g * g, T = P + 1 + NREG;
   const size_t M = size_t(B) * T;
   return align256(M * D * 2) * 2        // residual stream x, scratch h
@@ -25,6 +26,9 @@ size_t vit_workspace_bytes(int B, int res) {
 int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int B, int res, int layer,
                 int feature_type, void* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   FP_REQUIRE(w != nullptr && w->layers != nullptr, "vit: null weights");
+  const int D = w->dim > 0 ? w->dim : 1024, HEADS = w->heads > 0 ? w->heads : 16, MLP = w->mlp_dim > 0 ? w->mlp_dim : 4096;
+  FP_REQUIRE((D == 1024 || D == 768) && HEADS * 64 == D && MLP % 256 == 0,
+             "vit: unsupported model %d / %d heads / MLP %d (ViT-L/14 and ViT-B/14, head dim 64)", D, HEADS, MLP);
   FP_REQUIRE(res > 0 && res % 14 == 0, "vit: crop resolution %d is not a multiple of the 14-pixel patch", res);
   FP_REQUIRE(layer >= 0 && layer <= w->depth, "vit: layer %d outside [0, %d]", layer, w->depth);
   FP_REQUIRE(w->pos_res == res, "vit: position embedding was prepared for %d px crops, got %d", w->pos_res, res);
@@ -34,12 +38,12 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
   const int g = res / 14, P = g * g, T = P + 1 + NREG;
   const size_t M = size_t(B) * T;
   FP_REQUIRE(M < (size_t(1) << 31) / 4, "vit: batch too large for one call");
-  FP_REQUIRE(workspace_bytes >= vit_workspace_bytes(B, res), "vit: workspace too small (%zu < %zu)", workspace_bytes,
-             vit_workspace_bytes(B, res));
+  FP_REQUIRE(workspace_bytes >= vit_workspace_bytes(D, MLP, B, res), "vit: workspace too small (%zu < %zu)",
+             workspace_bytes, vit_workspace_bytes(D, MLP, B, res));
   FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vit: workspace must be 256-byte aligned");
 
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  bf16* x = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
+  bf16* x = reinterpret_cast<bf16*>(ws); ws += align256(M * size_t(D) * 2);
   bf16* h = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
   bf16* qkv = reinterpret_cast<bf16*>(ws); ws += align256(M * 3 * D * 2);
   bf16* mlp = reinterpret_cast<bf16*>(ws); ws += align256(M * MLP * 2);

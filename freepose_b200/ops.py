@@ -39,9 +39,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int = FP_EP
 
 
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-6):
-    rows = x.numel() // 1024
+    D = x.shape[-1]
+    rows = x.numel() // D
     out = torch.empty_like(x)
-    check(load().fp_layernorm_bf16(ptr(x), ptr(w), ptr(b), ptr(out), rows, eps, rows, 0, rows, stream_ptr()),
+    check(load().fp_layernorm_bf16(ptr(x), ptr(w), ptr(b), ptr(out), rows, D, eps, rows, 0, rows, stream_ptr()),
           "fp_layernorm_bf16")
     return out
 

@@ -1,4 +1,4 @@
-"""Device-resident DINOv2 ViT-L/14-reg engine: packs a hub-format state dict for the C ABI and drives
+"""Device-resident DINOv2 ViT-L/14-reg (or ViT-B/14-reg) engine: packs a hub-format state dict for the C ABI and drives
 ``fp_vit_forward`` in image chunks over one reusable workspace."""
 from __future__ import annotations
 
@@ -25,8 +25,8 @@ class ViTEngine:
     def __init__(self, state_dict: dict, cfg: VitConfig = VITL14_REG, device="cuda", chunk: int = 256):
         if not torch.cuda.is_available():
             raise RuntimeError("ViTEngine needs a CUDA device (no CPU fallback)")
-        assert cfg.embed_dim == 1024 and cfg.num_heads == 16 and cfg.mlp_dim == 4096 and cfg.patch_size == 14, \
-            "the sm_100a kernels are specialised for ViT-L/14"
+        assert cfg.embed_dim in (1024, 768) and cfg.head_dim == 64 and cfg.mlp_dim % 256 == 0 and cfg.patch_size == 14, \
+            "the sm_100a kernels cover ViT-L/14 and ViT-B/14 (head dim 64)"
         self.cfg = cfg
         self.device = torch.device(device)
         self.depth = state_dict_depth(state_dict)
@@ -59,6 +59,7 @@ class ViTEngine:
             L.ls2 = put(sd[p + "ls2.gamma"])
         self._w = _lib.VitWeights()
         self._w.depth = self.depth
+        self._w.dim, self._w.heads, self._w.mlp_dim = cfg.embed_dim, cfg.num_heads, cfg.mlp_dim
         self._w.layers = C.cast(self._layers, C.POINTER(_lib.VitLayer))
         self._w.patch_w, self._w.patch_b = put(pw), put(sd["patch_embed.proj.bias"])
         self._w.norm_w, self._w.norm_b = put(sd["norm.weight"]), put(sd["norm.bias"])
@@ -82,7 +83,7 @@ class ViTEngine:
 
     def _workspace(self, batch: int, res: int) -> torch.Tensor:
         key = (batch, res)
-        need = self._lib.fp_vit_workspace_bytes(batch, res)
+        need = self._lib.fp_vit_workspace_bytes(self.cfg.embed_dim, self.cfg.mlp_dim, batch, res)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)

@@ -42,6 +42,8 @@ class VitConfig:
 
 
 VITL14_REG = VitConfig()
+# dinov2_vitb14_reg: the refiner's confidence model (reference tracking_refiner.py:20-23)
+VITB14_REG = VitConfig(embed_dim=768, depth=12, num_heads=12, mlp_dim=3072)
 
 
 def synthetic_state_dict(cfg: VitConfig = VITL14_REG, seed: int = 0, depth: int | None = None,

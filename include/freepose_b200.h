@@ -48,9 +48,11 @@ FP_API const char* fp_profile_kind_name(int kind);
 FP_API int fp_profile_collect(int kind, double* total_ms, double* total_work, long long* launches);
 
 /* ------------------------------------------------------------------------------------------------
- * DINOv2 ViT-L/14-reg feature extractor
+ * DINOv2 ViT-{L,B}/14-reg feature extractor (the shapes in the comments are ViT-L's: dim 1024, 16 heads, MLP 4096;
+ * ViT-B = 768 / 12 / 3072 is the model of tracking_refiner.py:20-23)
  * replaces: src/pipeline/retrieval/dino.py:14-32  (DINOv2FeatureExtractor.forward:
  *           Normalize -> prepare_tokens_with_masks -> blocks[:layer] -> norm -> token slice)
+ *           and hub forward_features()["x_norm_patchtokens"] (tracking_refiner.py:79,84) with layer = depth
  * ------------------------------------------------------------------------------------------------ */
 typedef struct fp_vit_layer {          /* all bf16; nn.Linear weights are [out, in] row-major        */
   const void *ln1_w, *ln1_b;           /* [1024]                                                     */
@@ -76,6 +78,8 @@ typedef struct fp_vit_weights {
                                           pos_embed for g = pos_res/14 (row 0 = cls position)        */
   const void* special_tokens;          /* [5, 1024] bf16: row 0 = bf16(cls_token + pos_embed[0]),
                                           rows 1..4 = register tokens                                */
+  int dim, heads, mlp_dim;             /* ABI 2: 1024/16/4096 (ViT-L) or 768/12/3072 (ViT-B); head dim is 64;
+                                          all three 0 = ViT-L                                        */
 } fp_vit_weights;
 
 enum { FP_INPUT_IMAGE_F32 = 0,   /* (B,3,res,res) fp32 in [0,1]; bf16 Normalize applied (dino.py:12,16) */
@@ -87,7 +91,7 @@ enum { FP_FEATURE_ALL = 0,       /* (B, 1+4+g*g, 1024)                          
        FP_FEATURE_REG = 2,       /* (B, 4, 1024)     dino.py:27-28                                      */
        FP_FEATURE_PATCH = 3 };   /* (B, g*g, 1024)   dino.py:29-30                                      */
 
-FP_API size_t fp_vit_workspace_bytes(int batch, int res);
+FP_API size_t fp_vit_workspace_bytes(int dim, int mlp_dim, int batch, int res);
 FP_API int fp_vit_forward(const fp_vit_weights* weights /* host struct */, const void* input, int input_kind,
                           int batch, int res, int layer, int feature_type, void* out_tokens_bf16,
                           void* workspace, size_t workspace_bytes, void* stream);
@@ -99,8 +103,8 @@ enum { FP_EPI_BIAS = 0, FP_EPI_BIAS_GELU = 1, FP_EPI_BIAS_LS_RES = 2, FP_EPI_PAT
 FP_API int fp_gemm_bf16(const void* A, int lda, const void* W, void* out, int ldo, int M, int N, int K, int mode,
                         const void* bias, const void* gamma, const void* residual_or_pos, int patches_per_img,
                         int tokens_per_img, int token_offset, void* stream);
-/* rows of 1024: y = bf16(((x-mean)*rstd)*w + b); replaces nn.LayerNorm(eps=1e-6) in the hub Block / norm */
-FP_API int fp_layernorm_bf16(const void* x, const void* w, const void* b, void* out, int rows, float eps,
+/* rows of dim (1024 or 768): y = bf16(((x-mean)*rstd)*w + b); replaces nn.LayerNorm(eps=1e-6) in the hub Block / norm */
+FP_API int fp_layernorm_bf16(const void* x, const void* w, const void* b, void* out, int rows, int dim, float eps,
                              int in_group_stride, int in_skip, int rows_per_group, void* stream);
 /* qkv [B*T, 3072] -> out [B*T, 1024]; replaces the hub (Mem-Eff)Attention core, 16 heads x 64 */
 FP_API int fp_attention_bf16(const void* qkv, void* out, int batch, int tokens, int heads, float scale,
@@ -182,6 +186,10 @@ typedef struct fp_raster_args {
                                top-down), or NULL = vertex colours only; colors may be NULL with a texture   */
   int tex_w, tex_h, tex_levels;
   const float* srgb_lut;    /* [65536] fp32: (i/65535)^2.2, pyrender's srgb_to_linear applied after filtering */
+  /* the refiner's render set-up (tracking_refiner.py:31-45): ambient 5, znear 1e-4 / zfar 9999, a camera per frame */
+  float ambient;            /* scene ambient light; 0 = 2.0 (renderer.py:53-55)                             */
+  float znear, zfar;        /* 0 = pyrender's IntrinsicsCamera defaults 0.05 / 100                           */
+  const float* view_k;      /* [B,4] fp32 per-view fx,fy,cx,cy (overrides the four scalars) or NULL          */
 } fp_raster_args;
 FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes /* host out */);
 FP_API int fp_rasterize(const fp_raster_args* args /* host struct */, void* workspace, size_t workspace_bytes,

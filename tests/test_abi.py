@@ -57,4 +57,5 @@ def test_argument_errors_are_reported_not_thrown(lib):
     assert lib.fp_raster_workspace_bytes(2, 10, 224, 3, ctypes.byref(n)) == -1
     assert b"msaa" in lib.fp_last_error()
     assert lib.fp_raster_workspace_bytes(2, 10, 224, 4, ctypes.byref(n)) == 0 and n.value > 2 * 224 * 224 * 4 * 8
-    assert lib.fp_vit_workspace_bytes(1, 224) > 261 * (1024 * 2 * 2 + 3072 * 2 + 4096 * 2)
+    assert lib.fp_vit_workspace_bytes(1024, 4096, 1, 224) > 261 * (1024 * 2 * 2 + 3072 * 2 + 4096 * 2)
+    assert lib.fp_vit_workspace_bytes(768, 3072, 1, 518) > 1374 * (768 * 2 * 2 + 2304 * 2 + 3072 * 2)

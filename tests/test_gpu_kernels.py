@@ -118,6 +118,16 @@ def test_layernorm(ops):
     check_stage(out, contract_layernorm(x.float(), w.float(), b.float(), 1e-6), "layernorm")
 
 
+def test_layernorm_768(ops):
+    from oracle.vit import contract_layernorm
+    torch.manual_seed(1)
+    x = (torch.randn(517, 768) * 1.5 - 0.2).to(bf)
+    w = (1 + 0.1 * torch.randn(768)).to(bf)
+    b = (0.1 * torch.randn(768)).to(bf)
+    out = ops.layernorm(x.to(dev), w.to(dev), b.to(dev))
+    check_stage(out, contract_layernorm(x.float(), w.float(), b.float(), 1e-6), "layernorm 768")
+
+
 @pytest.mark.parametrize("B,T", [(2, 261), (1, 17), (3, 272), (2, 256), (5, 128), (1, 129),
                                  # several (image, head) pairs per CTA: the cross-tile / cross-pair pipeline
                                  (40, 261), (30, 140), (24, 200), (40, 40), (21, 264)])

@@ -84,6 +84,32 @@ def test_vit_reference_native_420_crops(engine2, sd2):
     assert rel_l2(e2, oc.norm(t2)[:, 5:]) < 2 * REL_BLOCK
 
 
+def test_vit_b14_reg_at_518_vs_oracle(lib):
+    """The refiner's confidence model (reference tracking_refiner.py:20-27: dinov2_vitb14_reg at 518^2 = 37x37 patches +
+    5 = 1374 tokens, native pos-embed grid): dim 768, 12 heads, MLP 3072 through the same kernels."""
+    from freepose_b200.vit_engine import ViTEngine
+    from freepose_b200.vit_weights import VITB14_REG, synthetic_state_dict
+    from oracle.pipeline import reference_normalize
+    from oracle.vit import OracleViT
+    sd = synthetic_state_dict(VITB14_REG, seed=3, depth=2)
+    torch.manual_seed(2)
+    img = torch.rand(2, 3, 518, 518)
+    oc = OracleViT(sd, VITB14_REG, contract=True)
+    with torch.no_grad():
+        xn = reference_normalize(img.to(bf)).float()
+        t0 = oc.prepare_tokens_with_masks(xn)
+        t1 = oc.blocks[0](t0)
+        t2 = oc.blocks[1](t1)
+    eng = ViTEngine(sd, VITB14_REG, chunk=2)
+    e0 = eng.forward(img.to(dev), layer=0, feature_type="all")
+    assert e0.shape == (2, 1374, 768)
+    assert rel_l2(e0, oc.norm(t0)) < 1e-3
+    assert rel_l2(eng.forward(img.to(dev), layer=1, feature_type="all"), oc.norm(t1)) < REL_BLOCK
+    e2 = eng.forward(img.to(dev), layer=2, feature_type="patch")
+    assert e2.shape == (2, 1369, 768)
+    assert rel_l2(e2, oc.norm(t2)[:, 5:]) < 2 * REL_BLOCK
+
+
 def test_vit_full_depth_22_vs_oracle(lib):
     """One 224^2 crop through all 22 blocks (the reference's layer) against the contract oracle, the eager-bf16
     oracle and fp32 ground truth."""
