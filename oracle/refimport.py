@@ -39,6 +39,7 @@ def install_stubs():
     _stub("pyrender", IntrinsicsCamera=None, OffscreenRenderer=None, Mesh=None, Scene=None)
     _stub("pyrender.constants", RenderFlags=rf)
     _stub("trimesh", Trimesh=type("Trimesh", (), {}), PointCloud=type("PointCloud", (), {}))
+    _stub("open3d")
 
 
 class _RefPath:
@@ -49,11 +50,17 @@ class _RefPath:
         self._saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
         for k in self._saved:
             del sys.modules[k]
-        sys.path.insert(0, str(REFERENCE_ROOT))
+        # The reference's ``src`` has no __init__.py (a namespace package), so ANY regular ``src`` package on sys.path
+        # -- this repository's overlay -- would win regardless of order: take those entries off the path meanwhile.
+        self._path = list(sys.path)
+        import os
+        sys.path[:] = [str(REFERENCE_ROOT)] + [p for p in sys.path
+                                               if not os.path.exists(os.path.join(p or os.getcwd(), "src", "__init__.py"))]
+        importlib.invalidate_caches()
         return self
 
     def __exit__(self, *exc):
-        sys.path.remove(str(REFERENCE_ROOT))
+        sys.path[:] = self._path
         self.loaded = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
         for k in self.loaded:
             del sys.modules[k]
@@ -67,7 +74,10 @@ def import_reference(module: str):
         raise RuntimeError("/root/reference is not present (GPU box?)")
     install_stubs()
     with _RefPath():
-        return importlib.import_module(module)
+        mod = importlib.import_module(module)
+    if not str(getattr(mod, "__file__", "")).startswith(str(REFERENCE_ROOT)):
+        raise RuntimeError(f"{module} resolved to {mod.__file__}, not to the reference checkout")
+    return mod
 
 
 def reference_feature_extractor(hub_model):
