@@ -78,6 +78,9 @@ SIGNATURES = {
     "fp_mask_bbox": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fp_crop_resize_pad": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "fp_depth_extents": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "fp_roi_align": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "fp_depth_mask_cubic": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "fp_patch_cosine": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -156,4 +156,19 @@ FP_API int fp_depth_extents(const float* depth, const int32_t* view_idx, int n, 
   return fp::depth_extents(depth, view_idx, n, res, kinv, out, S(stream));
 }
 
+FP_API int fp_roi_align(const float* image, int channels, int height, int width, const float* boxes, int n, int out_h,
+                        int out_w, int sampling_ratio, float* out, void* stream) {
+  return fp::roi_align(image, channels, height, width, boxes, n, out_h, out_w, sampling_ratio, out, S(stream));
+}
+
+FP_API int fp_depth_mask_cubic(const float* depth, int B, int res, int src_stride, int g, uint8_t* mask_out,
+                               void* stream) {
+  return fp::depth_mask_cubic(depth, B, res, src_stride, g, mask_out, S(stream));
+}
+
+FP_API int fp_patch_cosine(const void* feats_a, const void* feats_b, const uint8_t* mask, int rows, int dim, float* out,
+                           void* stream) {
+  return fp::patch_cosine(B16(feats_a), B16(feats_b), mask, rows, dim, out, S(stream));
+}
+
 }  // extern "C"

@@ -124,6 +124,12 @@ int crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, co
 int depth_extents(const float* depth, const int32_t* view_idx, int n_out, int res, const double* kinv_dev,
                   double* out, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------- refiner confidence pass
+int roi_align(const float* image, int C, int H, int W, const float* boxes, int n, int out_h, int out_w,
+              int sampling_ratio, float* out, cudaStream_t stream);
+int depth_mask_cubic(const float* depth, int B, int res, int stride, int g, uint8_t* mask, cudaStream_t stream);
+int patch_cosine(const bf16* a, const bf16* b, const uint8_t* mask, int rows, int D, float* out, cudaStream_t stream);
+
 }  // namespace fp
 
 // ---------------------------------------------------------------------------------------- ViT

@@ -215,10 +215,12 @@ def srgb_lut(device) -> torch.Tensor:
 
 
 def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors, poses: torch.Tensor, fx, fy, cx, cy,
-              res: int, msaa: int = 4, cull_backfaces: bool = False, uv=None, texture=None, points: bool = False):
+              res: int, msaa: int = 4, cull_backfaces: bool = False, uv=None, texture=None, points: bool = False,
+              ambient: float = 0.0, znear: float = 0.0, zfar: float = 0.0, view_k=None):
     """verts (V,3) fp32, faces (F,3) int32, colors (V,3) u8 | None, poses (B,4,4)|(B,3,4) fp32 -> rgb u8 (B,res,res,3),
     depth fp32 (B,res,res).  ``texture`` = (RGBA8 mip chain u8 tensor, w, h, levels) with ``uv`` (V,2) fp32;
-    ``points`` renders the vertices as 1-pixel point sprites (faces ignored)."""
+    ``points`` renders the vertices as 1-pixel point sprites (faces ignored).  ``ambient`` / ``znear`` / ``zfar``: 0 = the
+    renderer.py defaults (2, 0.05, 100); ``view_k`` (B,4) fp32 = per-view fx,fy,cx,cy."""
     dev = verts.device
     B = poses.shape[0]
     p34 = poses[:, :3, :4].to(torch.float32).contiguous()
@@ -237,12 +239,15 @@ def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors, poses: torch.Ten
     args = _lib.RasterArgs(ptr(verts), ptr(faces), ptr(colors), V, F, ptr(p34), B, float(fx), float(fy), float(cx),
                            float(cy), res, msaa, int(cull_backfaces), ptr(gamma_lut(dev)), ptr(rgb), ptr(depth),
                            int(points), ptr(uv) if texture is not None else None, ptr(chain), int(tw), int(th), int(tl),
-                           ptr(srgb_lut(dev)) if texture is not None else None)
+                           ptr(srgb_lut(dev)) if texture is not None else None, float(ambient), float(znear), float(zfar),
+                           ptr(view_k))
+    if view_k is not None:
+        assert view_k.dtype == torch.float32 and view_k.shape == (B, 4)
     check(lib.fp_rasterize(C.byref(args), ptr(ws), ws.numel(), stream_ptr()), "fp_rasterize")
     return rgb, depth
 
 
-def rasterize_mesh(mesh, poses: torch.Tensor, fx, fy, cx, cy, res: int, msaa: int = 4, cull_backfaces: bool = False):
+def rasterize_mesh(mesh, poses: torch.Tensor, fx, fy, cx, cy, res: int, msaa: int = 4, cull_backfaces: bool = False, **kw):
     """Any :class:`pipeline.utils.Mesh` (vertex-coloured, textured or point cloud) -> rgb, depth."""
     from .pipeline.utils import mesh_texture_to_device, mesh_to_device
     dev = poses.device
@@ -250,8 +255,8 @@ def rasterize_mesh(mesh, poses: torch.Tensor, fx, fy, cx, cy, res: int, msaa: in
     tex = mesh_texture_to_device(mesh, dev)
     if tex is not None:
         return rasterize(v, f, c, poses, fx, fy, cx, cy, res, msaa, cull_backfaces, uv=tex["uv"],
-                         texture=(tex["chain"], tex["w"], tex["h"], tex["levels"]))
-    return rasterize(v, f, c, poses, fx, fy, cx, cy, res, msaa, cull_backfaces, points=mesh.is_point_cloud)
+                         texture=(tex["chain"], tex["w"], tex["h"], tex["levels"]), **kw)
+    return rasterize(v, f, c, poses, fx, fy, cx, cy, res, msaa, cull_backfaces, points=mesh.is_point_cloud, **kw)
 
 
 # ------------------------------------------------------------------------------------------- geometry
@@ -324,4 +329,41 @@ def depth_extents(depth: torch.Tensor, K, view_idx=None):
     out = torch.empty(n, 8, dtype=torch.float64, device=dev)
     check(load().fp_depth_extents(ptr(depth), ptr(view_idx), n, res, ptr(kinv), ptr(out), stream_ptr()),
           "fp_depth_extents")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- refiner confidence pass
+def roi_align(image: torch.Tensor, boxes: torch.Tensor, out_h: int, out_w: int, sampling_ratio: int = 2):
+    """torchvision.ops.roi_align(image[None], [0 | boxes], (out_h, out_w), sampling_ratio=...) for one (C,H,W) fp32
+    image and (n,4) fp32 xyxy boxes -> (n,C,out_h,out_w) fp32 (reference refiner_utils.py:128-133)."""
+    assert image.dtype == torch.float32 and image.dim() == 3 and boxes.dtype == torch.float32 and boxes.shape[1] == 4
+    Cn, H, W = image.shape
+    n = boxes.shape[0]
+    out = torch.empty(n, Cn, out_h, out_w, dtype=torch.float32, device=image.device)
+    check(load().fp_roi_align(ptr(image.contiguous()), Cn, H, W, ptr(boxes.contiguous()), n, out_h, out_w,
+                              sampling_ratio, ptr(out), stream_ptr()), "fp_roi_align")
+    return out
+
+
+def depth_mask_cubic(depth: torch.Tensor, g: int, res: int | None = None):
+    """(B,S,S) fp32 depth, image = its top-left res x res (default S) -> (B,g,g) bool:
+    cv2.resize((depth > 0).astype(float32), (g,g), INTER_CUBIC) > 0.5 (reference tracking_refiner.py:75)."""
+    B, S, _ = depth.shape
+    res = S if res is None else res
+    mask = torch.empty(B, g, g, dtype=torch.uint8, device=depth.device)
+    check(load().fp_depth_mask_cubic(ptr(depth.contiguous()), B, res, S, g, ptr(mask), stream_ptr()),
+          "fp_depth_mask_cubic")
+    return mask.bool()
+
+
+def patch_cosine(feats_a: torch.Tensor, feats_b: torch.Tensor, mask: torch.Tensor | None = None):
+    """(..., D) bf16 token rows x 2 (+ optional bool/u8 mask over the rows) -> (...) fp32 masked cosine
+    (reference tracking_refiner.py:80-88)."""
+    assert feats_a.shape == feats_b.shape and feats_a.dtype == bf16 and feats_b.dtype == bf16
+    D = feats_a.shape[-1]
+    rows = feats_a.numel() // D
+    m = None if mask is None else mask.to(torch.uint8).contiguous()
+    out = torch.empty(feats_a.shape[:-1], dtype=torch.float32, device=feats_a.device)
+    check(load().fp_patch_cosine(ptr(feats_a.contiguous()), ptr(feats_b.contiguous()), ptr(m), rows, D, ptr(out),
+                                 stream_ptr()), "fp_patch_cosine")
     return out

@@ -217,6 +217,26 @@ FP_API int fp_crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t*
 FP_API int fp_depth_extents(const float* depth, const int32_t* view_idx, int n, int res, const double* kinv,
                             double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Refiner pose-confidence pass: tracking_refiner.py:70-100 = roi_align crop of the photo
+ * at 518^2, one render at the cropped K (fp_rasterize with ambient 5, view_k), ViT-B/14-reg on both
+ * (fp_vit_forward, layer = depth), masked per-patch cosine.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: torchvision.ops.roi_align(image[None], boxes, (out_h,out_w), sampling_ratio=2) in
+ * src/pipeline/refiner_utils.py:128-133.  image (C,H,W) fp32, boxes (n,4) fp32 x1,y1,x2,y2 on the device,
+ * out (n,C,out_h,out_w) fp32; spatial_scale 1, aligned=False. */
+FP_API int fp_roi_align(const float* image, int channels, int height, int width, const float* boxes, int n, int out_h,
+                        int out_w, int sampling_ratio, float* out, void* stream);
+/* replaces: cv2.resize((depth > 0).astype(float32), (g,g), INTER_CUBIC) > 0.5, tracking_refiner.py:75.
+ * depth (B,src_stride,src_stride) fp32 of which the top-left res x res is the image (the rasteriser renders 518 px
+ * views into 520 px targets) -> mask_out (B,g,g) u8 */
+FP_API int fp_depth_mask_cubic(const float* depth, int B, int res, int src_stride, int g, uint8_t* mask_out,
+                               void* stream);
+/* replaces: tracking_refiner.py:80-88.  feats_a, feats_b (rows, dim) bf16 token rows, mask (rows) u8 or NULL ->
+ * out (rows) fp32 = mask * cos(a, b) */
+FP_API int fp_patch_cosine(const void* feats_a, const void* feats_b, const uint8_t* mask, int rows, int dim, float* out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

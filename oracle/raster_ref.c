@@ -19,7 +19,7 @@
 
 #define SUB 8
 #define ONE 256
-static const float ZNEAR = 0.05f, ZFAR = 100.0f;
+static float ZNEAR = 0.05f, ZFAR = 100.0f;   /* pyrender IntrinsicsCamera defaults; raster_ref3 may override per call */
 #define COORD_LIMIT (1 << 22)
 
 typedef struct { int x, y, ok; float z, iz; } SV;
@@ -54,6 +54,7 @@ typedef struct {
   const uint8_t* gamma_lut; /* [65536] */
   int tex_w, tex_h, tex_levels;
   int points;
+  float ambient, ambient_255;
 } Surface;
 
 static int to_unorm8(float lin, const uint8_t* lut) {
@@ -122,7 +123,7 @@ static void shade(const Surface* sf, const int32_t* faces, const SV* sv, int f, 
     for (int ch = 0; ch < 3; ++ch)
       vc[ch] = interp(w, (float)sf->colors[3 * i0 + ch], (float)sf->colors[3 * i1 + ch], (float)sf->colors[3 * i2 + ch]);
   if (sf->texture == NULL) {
-    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(vc[ch] * (2.0f / 255.0f), sf->gamma_lut);
+    for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(vc[ch] * sf->ambient_255, sf->gamma_lut);
     return;
   }
   float ua = sf->uv[2 * i0], ub = sf->uv[2 * i1], uc = sf->uv[2 * i2];
@@ -149,7 +150,7 @@ static void shade(const Surface* sf, const int32_t* faces, const SV* sv, int f, 
     if (!(cn == cn)) cn = 0.f;
     float lin = sf->srgb_lut[(int)(cn * 65535.0f + 0.5f)];
     if (sf->colors != NULL) lin = lin * (vc[ch] / 255.0f);
-    out[ch] = to_unorm8(lin * 2.0f, sf->gamma_lut);
+    out[ch] = to_unorm8(lin * sf->ambient, sf->gamma_lut);
   }
 }
 
@@ -224,7 +225,7 @@ static void render_view(const float* verts, const int32_t* faces, const Surface*
         if (f < 0) continue;
         int col[3];
         if (sf->points)
-          for (int ch = 0; ch < 3; ++ch) col[ch] = to_unorm8((float)sf->colors[3 * f + ch] * (2.0f / 255.0f), sf->gamma_lut);
+          for (int ch = 0; ch < 3; ++ch) col[ch] = to_unorm8((float)sf->colors[3 * f + ch] * sf->ambient_255, sf->gamma_lut);
         else
           shade(sf, faces, sv, f, px, py, col);
         for (int ch = 0; ch < 3; ++ch) acc[ch] += col[ch];
@@ -235,22 +236,37 @@ static void render_view(const float* verts, const int32_t* faces, const Surface*
     }
 }
 
-int raster_ref2(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
+int raster_ref3(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
                 int B, float fx, float fy, float cx, float cy, int res, int msaa, int cull, const uint8_t* lut,
                 uint8_t* rgb, float* depth, int points, const float* uv, const uint8_t* texture, int tex_w, int tex_h,
-                int tex_levels, const float* srgb_lut) {
+                int tex_levels, const float* srgb_lut, float ambient, float znear, float zfar, const float* view_k) {
   if (msaa != 1 && msaa != 4) return -1;
   if (texture == NULL && colors == NULL) return -3;
-  Surface sf = {colors, uv, texture, srgb_lut, lut, tex_w, tex_h, tex_levels, points};
+  Surface sf = {colors, uv, texture, srgb_lut, lut, tex_w, tex_h, tex_levels, points, 0.f, 0.f};
+  sf.ambient = ambient > 0.f ? ambient : 2.0f;
+  sf.ambient_255 = sf.ambient / 255.0f;
+  ZNEAR = znear > 0.f ? znear : 0.05f;
+  ZFAR = zfar > 0.f ? zfar : 100.0f;
   SV* sv = (SV*)malloc(sizeof(SV) * (size_t)V);
   float* zbuf = (float*)malloc(sizeof(float) * (size_t)res * res * msaa);
   int32_t* fbuf = (int32_t*)malloc(sizeof(int32_t) * (size_t)res * res * msaa);
   if (!sv || !zbuf || !fbuf) return -2;
-  for (int b = 0; b < B; ++b)
+  for (int b = 0; b < B; ++b) {
+    if (view_k != NULL) { fx = view_k[4 * b]; fy = view_k[4 * b + 1]; cx = view_k[4 * b + 2]; cy = view_k[4 * b + 3]; }
     render_view(verts, faces, &sf, V, F, poses + (size_t)b * 12, fx, fy, cx, cy, res, msaa, cull,
                 rgb + (size_t)b * res * res * 3, depth + (size_t)b * res * res, sv, zbuf, fbuf);
+  }
   free(sv); free(zbuf); free(fbuf);
+  ZNEAR = 0.05f; ZFAR = 100.0f;
   return 0;
+}
+
+int raster_ref2(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,
+                int B, float fx, float fy, float cx, float cy, int res, int msaa, int cull, const uint8_t* lut,
+                uint8_t* rgb, float* depth, int points, const float* uv, const uint8_t* texture, int tex_w, int tex_h,
+                int tex_levels, const float* srgb_lut) {
+  return raster_ref3(verts, faces, colors, V, F, poses, B, fx, fy, cx, cy, res, msaa, cull, lut, rgb, depth, points, uv,
+                     texture, tex_w, tex_h, tex_levels, srgb_lut, 0.f, 0.f, 0.f, NULL);
 }
 
 int raster_ref(const float* verts, const int32_t* faces, const uint8_t* colors, int V, int F, const float* poses,

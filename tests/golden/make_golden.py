@@ -163,6 +163,60 @@ def golden_retrieval():
     np.savez_compressed(OUT / "retrieval.npz", **store)
 
 
+def golden_refiner():
+    """The reference's OWN TrackingRefiner.pose_confidence / crop_image / update_K_with_crop /
+    _get_threshold_for_confidence, unmodified; torch.hub.load returns the hub-shaped oracle ViT-B (2 blocks, seeded
+    synthetic weights) and _render -- pyrender, not installable -- is replaced by the C raster restatement."""
+    from PIL import Image
+    from freepose_b200.vit_weights import VITB14_REG, synthetic_state_dict
+    from oracle import refiner as OR
+    from oracle.vit import OracleViT
+    sd = synthetic_state_dict(VITB14_REG, seed=3, depth=2)
+
+    class Hub(OracleViT):                       # what torch.hub's DinoVisionTransformer exposes to the refiner
+        def forward_features(self, x):
+            return {"x_norm_patchtokens": OracleViT.forward_features(self, x, len(self.blocks))[:, 5:]}
+
+    hub = Hub(sd, VITB14_REG)
+    tr = refimport.import_reference("src.pipeline.estimators.tracking_refiner")
+    ru = sys.modules.get("src.pipeline.refiner_utils") or refimport.import_reference("src.pipeline.refiner_utils")
+    ru = tr.refiner_utils
+    orig = torch.hub.load
+    torch.hub.load = lambda repo, name, *a, **k: hub if "dinov2" in repo else torch.nn.Identity()
+    try:
+        ref = tr.TrackingRefiner(dino_device="cpu", cotracker_device="cpu")
+    finally:
+        torch.hub.load = orig
+    assert ref.image_size == 518 and ref.feats_size == 37
+    ref._render = lambda m, w, h, K, T: OR.render(m, K, T, w)          # the one replaced piece
+    rng = np.random.default_rng(11)
+    store = {}
+    confs = []
+    for i in range(2):
+        mesh, frame, K, T = OR.synthetic_case(i)
+        conf = ref.pose_confidence(mesh, Image.fromarray(frame), K, T)
+        crop, bbox, new_K = ref._crop_image(mesh, Image.fromarray(frame), K, T)
+        store[f"frame_{i}_sha"], store[f"T_{i}"] = sha(frame), T
+        store[f"conf_{i}"], store[f"bbox_{i}"], store[f"new_K_{i}"] = conf, bbox.numpy(), new_K.numpy()
+        store[f"crop_{i}_rows"] = crop[:, ::37, ::37].numpy()          # a 14x14 lattice of the 518^2 crop per channel
+        store[f"crop_{i}_sha"] = sha(crop.numpy())
+        confs.append(conf)
+    store["K"] = K
+    store["thr"] = np.float64(ref._get_threshold_for_confidence(np.stack(confs)))
+    sim = rng.uniform(-0.2, 1.0, size=(5, 37, 37)).astype(np.float32)
+    store["sim"], store["sim_thr"] = sim, np.float64(ref._get_threshold_for_confidence(sim))
+    # crop_image / update_K_with_crop on a batch of poses (the reference functions themselves)
+    pts = torch.from_numpy(np.pad(rng.normal(scale=0.05, size=(100, 3)), ((0, 0), (0, 1)), constant_values=1.)).float()
+    Ts = torch.eye(4).repeat(3, 1, 1); Ts[:, 2, 3] = torch.tensor([0.5, 0.8, 1.3]); Ts[:, 0, 3] = torch.tensor([0.0, 0.1, -0.2])
+    img = torch.from_numpy(rng.random((3, 120, 160)).astype(np.float32))
+    Kt = torch.tensor([[200.0, 0, 80], [0, 200.0, 60], [0, 0, 1]])
+    crops, boxes = ru.crop_image(img, Ts, pts, Kt, 64, 48)
+    store["ci_pts"], store["ci_Ts"], store["ci_img"], store["ci_K"] = pts.numpy(), Ts.numpy(), img.numpy(), Kt.numpy()
+    store["ci_crops"], store["ci_boxes"] = crops.numpy(), boxes.numpy()
+    store["ci_newK"] = ru.update_K_with_crop(Kt, boxes, 64, 48).numpy()
+    np.savez_compressed(OUT / "refiner.npz", **store)
+
+
 if __name__ == "__main__":
     assert refimport.available(), "/root/reference is required to mint fixtures"
     torch.set_num_threads(1)
@@ -172,5 +226,6 @@ if __name__ == "__main__":
     golden_dino_forward()
     golden_score()
     golden_retrieval()
+    golden_refiner()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
