@@ -217,6 +217,44 @@ def golden_refiner():
     np.savez_compressed(OUT / "refiner.npz", **store)
 
 
+def template_store_case(n_views):
+    """Seeded renders for the template-store fixture (shared with tests/test_template_store.py)."""
+    from freepose_b200.pipeline.utils import generate_poses
+    from freepose_b200.synthetic import synthetic_mesh
+    from oracle import raster as R
+    out = {}
+    for j, mesh_id in enumerate(("mesh_a_1", "b2")):
+        m = synthetic_mesh(7 + j, subdivisions=1 + j)
+        poses = np.array(generate_poses(600))[:n_views]
+        if j == 1:
+            poses[3, 2, 3] = 40.0            # a view with a tiny mask: the reader forces the centre square
+        out[mesh_id] = R.render_mesh(m, poses, 600, 600, 210, 210, 420, msaa=1)
+    return out
+
+
+def golden_template_store():
+    """Shards written by THIS repository's TemplateShardWriter, read back by the reference's OWN WebTemplateDataset
+    (src/dataloader/template.py, unmodified; it hard-codes 600 views per mesh)."""
+    import tempfile
+    from freepose_b200.pipeline.template_store import TemplateShardWriter
+    tm = refimport.import_reference("src.dataloader.template")
+    d = Path(tempfile.mkdtemp())
+    with TemplateShardWriter(d) as w:
+        for mesh_id, (rgb, depth) in template_store_case(600).items():
+            w.write_mesh(mesh_id, rgb, depth)
+    (d / "list.csv").write_text("model_name\nmesh_a_1\nb2\n")
+    ds = tm.WebTemplateDataset(d.as_posix(), (d / "list.csv").as_posix(), crop=False)
+    store = {}
+    for name in ("mesha1", "b2"):
+        o = ds.get_template_by_name(name)
+        assert o["templates"].shape == (600, 3, 420, 420)
+        for k in ("templates", "masks", "depths"):
+            store[f"{name}_{k}_sha40"] = sha(o[k][:40].numpy())
+        store[f"{name}_tar"], store[f"{name}_intrinsic"] = o["tar_file"], o["intrinsic"].numpy()
+        store[f"{name}_mask_counts40"] = o["masks"][:40].sum((1, 2)).numpy()
+    np.savez_compressed(OUT / "template_store.npz", **store)
+
+
 if __name__ == "__main__":
     assert refimport.available(), "/root/reference is required to mint fixtures"
     torch.set_num_threads(1)
@@ -227,5 +265,6 @@ if __name__ == "__main__":
     golden_score()
     golden_retrieval()
     golden_refiner()
+    golden_template_store()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
