@@ -8,17 +8,17 @@
 //                              exponentiating the current tile (the low half as soon as its columns have been consumed)
 //                              O = P V   (P read straight from TMEM -- "TS" form --, V as MN-major smem operand);
 //                              O is double buffered so a tile's normalisation/store is deferred into the next tile
-//   warp 2        TMEM allocator
 //   warps 4..11   softmax      two warps per TMEM lane quarter split the key columns of every row: row max,
 //                              p = exp2((s - max) * scale*log2e) in fp32, row sum of the unrounded p, P rounded to
 //                              bf16 and stored with tcgen05.st over the logit columns it was computed from (no extra
 //                              TMEM, no shared-memory round trip); O / rowsum -> bf16 -> HBM of the previous tile
 //                              runs between two exponential chunks of the current one.
-//   warps 12..15  tail queries token counts such as 261 = 2*128 + 5 leave a query tile with a handful of rows (cls +
+//   warps 2..3    tail queries token counts such as 261 = 2*128 + 5 leave a query tile with a handful of rows (cls +
 //                              registers).  As a tensor-core tile they cost as much as a full one (measured: T=261
-//                              took 1.83x the time of T=256), so remainders of <= 8 rows are computed on the CUDA cores
-//                              by four otherwise idle warps, straight from the K/V already resident in shared memory
-//                              and completely decoupled from the TMEM / mbarrier pipeline of the full tiles.
+//                              took 1.83x the time of T=256), so remainders of <= 8 rows are computed by two otherwise
+//                              idle warps with mma.sync straight from the K/V already resident in shared memory,
+//                              completely decoupled from the TMEM / mbarrier pipeline of the full tiles (warp 2 also
+//                              allocates the TMEM).
 //
 // Arithmetic contract = flash/xformers attention (oracle/vit.py contract_attention): logits and softmax statistics
 // in fp32, un-normalised P rounded to bf16 before P.V (fp32 accumulate), one rounding of O.
@@ -41,8 +41,8 @@ constexpr int KV_BYTES = MAX_TPAD * ROW_BYTES;  // 34 KB
 constexpr int TAIL_MAX = 8;        // remainder query rows handled by the CUDA-core tail warps
 constexpr int TAIL_BOX = 16;       // rows per tail-Q TMA box
 constexpr int NUM_SOFTMAX_WARPS = 8;
-constexpr int NUM_TAIL_WARPS = 4;
-constexpr int NUM_THREADS = 128 + (NUM_SOFTMAX_WARPS + NUM_TAIL_WARPS) * 32;
+constexpr int NUM_TAIL_WARPS = 2;     // warps 2 and 3
+constexpr int NUM_THREADS = 128 + NUM_SOFTMAX_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0;      // 272 fp32 logit columns; bf16x2 P overwrites the first half of every consumed 32-column group
 constexpr int O_COL = 272;    // 2 x 64 fp32 columns (double buffered across tiles)
@@ -133,6 +133,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+
+  // The specialised instance keeps three of a row share's four 32-logit groups in registers between the max and the
+  // exponential pass (TMEM reads run at 64 B/clk per scheduler: reading S twice was the floor of this kernel).  With
+  // 12 warps every thread may use 168 registers, which is enough without warpgroup register reallocation.
+  constexpr bool kSingleRead = T_CONST == 261;
 
   if (warp == 0) {
     // ---------------------------------------------------------------------------- TMA loader
@@ -340,99 +345,177 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int t = 0; t < tiles_per_pair; ++t, ++g) {
         const uint32_t par = g & 1;
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
-        if (timing) { tk0 = clock64(); tepi = 0; }
-        if (stamping && g == 11) stamp[0] = clock64();
-        mbar_wait(&s_full[0], par);
-        tc_fence_after();
-        if (stamping && g == 11) stamp[1] = clock64();
-        if (timing) tk1 = clock64();
-        int parts_ready = 1;             // the key parts of S arrive on their own barriers, in order
-        auto need_part = [&](int part) {
-          while (parts_ready <= part) {
-            mbar_wait(&s_full[parts_ready], par);
-            tc_fence_after();
-            if (stamping && g == 11) stamp[1 + parts_ready] = clock64();
-            ++parts_ready;
-          }
-        };
-        const bool warp_active = kAllRowsLive || t * QT + q * 32 < T - n_tail;  // any query row of this warp in the tile
-        // Key columns are dealt in 64-column chunks: chunk c of this warp = columns [64c + 32hf, +32) (the last one
-        // may hold 16).  In the specialised instance both passes are software pipelined: the TMEM load of chunk c+1
-        // is in flight while chunk c is reduced / exponentiated (two register buffers, chunk loop unrolled by hand).
-        // The run-time-T instance keeps load -> wait -> compute: there the second buffer only costs registers
-        // (measured: 0.61 ms with the pipeline vs 0.52 ms without, B=521, T=261 forced through it).
-        constexpr bool kPrefetch = T_CONST != 0;
-        auto chunk_exists = [&](int c) { return warp_active && c < nchunks && c * 64 + hf * 32 < tpad; };
-        auto issue_ld = [&](int c, uint32_t (&v)[32]) {
-          const int c0 = c * 64 + hf * 32;
-          if (tpad - c0 >= 32) {
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
-          } else {
-            tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-#pragma unroll
-            for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
-          }
-        };
-        uint32_t va[32], vb[32];
-        // ---- pass 1: row max
-        float m = -INFINITY;
-        auto max_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
-          if (!chunk_exists(c)) return;
-          need_part(((kPrefetch ? c + 1 : c) * 64) / S_PART < 2 ? ((kPrefetch ? c + 1 : c) * 64) / S_PART : 2);
-          if (!kPrefetch) { issue_ld(c, cur); tmem_ld_wait(); }
-          const bool more = kPrefetch && chunk_exists(c + 1);
-          if (more) issue_ld(c + 1, nxt);
-          const int c0 = c * 64 + hf * 32;
-          if (c0 + 32 <= T) m = max_group<false>(cur, 32, m);
-          else                m = max_group<true>(cur, T - c0, m);
-          if (more) tmem_ld_wait();
-        };
-        if (kPrefetch && chunk_exists(0)) { issue_ld(0, va); tmem_ld_wait(); }
-        max_step(0, va, vb); max_step(1, vb, va); max_step(2, va, vb); max_step(3, vb, va); max_step(4, va, vb);
-        need_part(2);   // (every tile consumes one phase of all three barriers, whatever its chunk count)
-        if (stamping && g == 11) stamp[4] = clock64();
-        if (timing) tk2 = clock64();
-        if (kPrefetch && chunk_exists(0)) issue_ld(0, va);  // pass 2's first chunk travels during the max exchange
-        // exchange buffers alternate with the tile parity: the partner warp may already be a phase ahead, and the
-        // row sums written at the end of this tile are read one tile later (deferred epilogue)
-        xch_max[par * 256 + hf * 128 + r] = m;
-        named_bar_sync(1 + q, 64);
-        m = fmaxf(xch_max[par * 256 + r], xch_max[par * 256 + 128 + r]);
-        const float msl = m * p.sl2;
-        if (kPrefetch && chunk_exists(0)) tmem_ld_wait();
-        if (timing) tk3 = clock64();
-        // ---- pass 2: exponentials, row sum, bf16 P into TMEM over the logits just consumed
         float l = 0.f;
-        auto exp_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
-          if (c >= nchunks) return;
-          const bool have = chunk_exists(c), more = kPrefetch && chunk_exists(c + 1);
-          if (!kPrefetch && have) { issue_ld(c, cur); tmem_ld_wait(); }
-          if (more) issue_ld(c + 1, nxt);
-          if (have) {
-            const int c0 = c * 64 + hf * 32;
-            uint32_t pk[16];
-            if (c0 + 32 <= T) l += exp_group<false, POLY>(cur, p.sl2, msl, 32, pk);
-            else                l += exp_group<true, POLY>(cur, p.sl2, msl, T - c0, pk);
-            if (tpad - c0 >= 32) {
-              tmem_st_32x32b_x16(tmem_base + lane_addr + S_COL + c0, pk);
-            } else {
-              tmem_st_32x32b_x8(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
-            }
+        if constexpr (kSingleRead) {
+          // ---- 261 tokens: this warp's logits are columns [64c + 32hf, +32) for c = 0..3 plus, for hf = 0, columns
+          // 256..263 (keys 256..260 are real).  One TMEM read into registers, max, exponentials from registers.
+          if (timing) { tk0 = clock64(); tepi = 0; }
+          // Registers hold three of the four 32-column groups between the passes; the fourth (and the 8-column tail) is
+          // reduced first and read again while the others are exponentiated (176 instead of 272 columns read per row).
+          uint32_t s0[32], s1[32], s2[32], s3[32], s4[8];
+          const uint32_t sbase = tmem_base + lane_addr + S_COL + hf * 32;
+          mbar_wait(&s_full[0], par);
+          tc_fence_after();
+          if (timing) tk1 = clock64();
+          tmem_ld_32x32b_x32(sbase, s0);
+          tmem_ld_32x32b_x32(sbase + 64, s1);
+          mbar_wait(&s_full[1], par);
+          tc_fence_after();
+          tmem_ld_32x32b_x32(sbase + 128, s2);
+          tmem_ld_32x32b_x32(sbase + 192, s3);
+          mbar_wait(&s_full[2], par);
+          tc_fence_after();
+          if (hf == 0) tmem_ld_32x32b_x8(tmem_base + lane_addr + S_COL + 256, s4);
+          tmem_ld_wait();
+          float m = max_group<false>(s3, 32, -INFINITY);     // group 3 and the tail die here ...
+          if (hf == 0) {
+#pragma unroll
+            for (int j = 0; j < T_CONST - 256; ++j) m = fmaxf(m, __uint_as_float(s4[j]));
           }
-          if (more) tmem_ld_wait();
-          if (have) tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[c]);
-          if (stamping && g == 10) stamp[8 + c] = clock64();
-        };
-        // the two warps of a scheduler take the owed epilogue at different chunks: while one sits in its latencies the
-        // other keeps the MUFU busy
-        exp_step(0, va, vb);
-        if (g > 0 && hf == 0) epilogue(g - 1, pb, ph, pt);
-        exp_step(1, vb, va); exp_step(2, va, vb);
-        if (g > 0 && hf == 1) epilogue(g - 1, pb, ph, pt);
-        exp_step(3, vb, va); exp_step(4, va, vb);
+          m = max_group<false>(s0, 32, m);
+          m = max_group<false>(s1, 32, m);
+          m = max_group<false>(s2, 32, m);
+          if (timing) tk2 = clock64();
+          xch_max[par * 256 + hf * 128 + r] = m;
+          named_bar_sync(1 + q, 64);
+          m = fmaxf(xch_max[par * 256 + r], xch_max[par * 256 + 128 + r]);
+          const float msl = m * p.sl2;
+          if (timing) tk3 = clock64();
+          // P of a chunk is published one chunk late: its tcgen05.st completes under the next chunk's exponentials
+          auto publish = [&](int c) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[c]);
+          };
+          uint32_t pk[16];
+          l += exp_group<false, POLY>(s0, p.sl2, msl, 32, pk);
+          tmem_st_32x32b_x16(sbase, pk);
+          tmem_ld_32x32b_x32(sbase + 192, s3);                                      // ... and are read a second time here
+          if (hf == 0) tmem_ld_32x32b_x8(tmem_base + lane_addr + S_COL + 256, s4);
+          l += exp_group<false, POLY>(s1, p.sl2, msl, 32, pk);
+          publish(0);
+          tmem_st_32x32b_x16(sbase + 64, pk);
+          if (g > 0 && hf == 0) epilogue(g - 1, pb, ph, pt);
+          l += exp_group<false, POLY>(s2, p.sl2, msl, 32, pk);
+          publish(1);
+          tmem_st_32x32b_x16(sbase + 128, pk);
+          tmem_ld_wait();
+          l += exp_group<false, POLY>(s3, p.sl2, msl, 32, pk);
+          publish(2);
+          tmem_st_32x32b_x16(sbase + 192, pk);
+          if (g > 0 && hf == 1) epilogue(g - 1, pb, ph, pt);
+          if (hf == 0) {
+            uint32_t p4[8];
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              e[j] = j < T_CONST - 256 ? ex2(fmaf(__uint_as_float(s4[j]), p.sl2, -msl)) : 0.f;
+              l += e[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { p4[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]); p4[4 + j] = 0u; }   // keys 264..271: P = 0
+            publish(3);
+            tmem_st_32x32b_x8(tmem_base + lane_addr + S_COL + 256, p4);
+            publish(4);
+          } else {
+            publish(3);
+            if (lane == 0) mbar_arrive(&p_full[4]);
+          }
+        } else {
+          if (timing) { tk0 = clock64(); tepi = 0; }
+          if (stamping && g == 11) stamp[0] = clock64();
+          mbar_wait(&s_full[0], par);
+          tc_fence_after();
+          if (stamping && g == 11) stamp[1] = clock64();
+          if (timing) tk1 = clock64();
+          int parts_ready = 1;             // the key parts of S arrive on their own barriers, in order
+          auto need_part = [&](int part) {
+            while (parts_ready <= part) {
+              mbar_wait(&s_full[parts_ready], par);
+              tc_fence_after();
+              if (stamping && g == 11) stamp[1 + parts_ready] = clock64();
+              ++parts_ready;
+            }
+          };
+          const bool warp_active = kAllRowsLive || t * QT + q * 32 < T - n_tail;  // any query row of this warp in the tile
+          // Key columns are dealt in 64-column chunks: chunk c of this warp = columns [64c + 32hf, +32) (the last one
+          // may hold 16).  In the specialised instance both passes are software pipelined: the TMEM load of chunk c+1
+          // is in flight while chunk c is reduced / exponentiated (two register buffers, chunk loop unrolled by hand).
+          // The run-time-T instance keeps load -> wait -> compute: there the second buffer only costs registers
+          // (measured: 0.61 ms with the pipeline vs 0.52 ms without, B=521, T=261 forced through it).
+          constexpr bool kPrefetch = T_CONST != 0;
+          auto chunk_exists = [&](int c) { return warp_active && c < nchunks && c * 64 + hf * 32 < tpad; };
+          auto issue_ld = [&](int c, uint32_t (&v)[32]) {
+            const int c0 = c * 64 + hf * 32;
+            if (tpad - c0 >= 32) {
+              tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + c0, v);
+            } else {
+              tmem_ld_32x32b_x16(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+  #pragma unroll
+              for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
+            }
+          };
+          uint32_t va[32], vb[32];
+          // ---- pass 1: row max
+          float m = -INFINITY;
+          auto max_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+            if (!chunk_exists(c)) return;
+            need_part(((kPrefetch ? c + 1 : c) * 64) / S_PART < 2 ? ((kPrefetch ? c + 1 : c) * 64) / S_PART : 2);
+            if (!kPrefetch) { issue_ld(c, cur); tmem_ld_wait(); }
+            const bool more = kPrefetch && chunk_exists(c + 1);
+            if (more) issue_ld(c + 1, nxt);
+            const int c0 = c * 64 + hf * 32;
+            if (c0 + 32 <= T) m = max_group<false>(cur, 32, m);
+            else                m = max_group<true>(cur, T - c0, m);
+            if (more) tmem_ld_wait();
+          };
+          if (kPrefetch && chunk_exists(0)) { issue_ld(0, va); tmem_ld_wait(); }
+          max_step(0, va, vb); max_step(1, vb, va); max_step(2, va, vb); max_step(3, vb, va); max_step(4, va, vb);
+          need_part(2);   // (every tile consumes one phase of all three barriers, whatever its chunk count)
+          if (stamping && g == 11) stamp[4] = clock64();
+          if (timing) tk2 = clock64();
+          if (kPrefetch && chunk_exists(0)) issue_ld(0, va);  // pass 2's first chunk travels during the max exchange
+          // exchange buffers alternate with the tile parity: the partner warp may already be a phase ahead, and the
+          // row sums written at the end of this tile are read one tile later (deferred epilogue)
+          xch_max[par * 256 + hf * 128 + r] = m;
+          named_bar_sync(1 + q, 64);
+          m = fmaxf(xch_max[par * 256 + r], xch_max[par * 256 + 128 + r]);
+          const float msl = m * p.sl2;
+          if (kPrefetch && chunk_exists(0)) tmem_ld_wait();
+          if (timing) tk3 = clock64();
+          // ---- pass 2: exponentials, row sum, bf16 P into TMEM over the logits just consumed
+          auto exp_step = [&](int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+            if (c >= nchunks) return;
+            const bool have = chunk_exists(c), more = kPrefetch && chunk_exists(c + 1);
+            if (!kPrefetch && have) { issue_ld(c, cur); tmem_ld_wait(); }
+            if (more) issue_ld(c + 1, nxt);
+            if (have) {
+              const int c0 = c * 64 + hf * 32;
+              uint32_t pk[16];
+              if (c0 + 32 <= T) l += exp_group<false, POLY>(cur, p.sl2, msl, 32, pk);
+              else                l += exp_group<true, POLY>(cur, p.sl2, msl, T - c0, pk);
+              if (tpad - c0 >= 32) {
+                tmem_st_32x32b_x16(tmem_base + lane_addr + S_COL + c0, pk);
+              } else {
+                tmem_st_32x32b_x8(tmem_base + lane_addr + S_COL + c0, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
+              }
+            }
+            if (more) tmem_ld_wait();
+            if (have) tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[c]);
+            if (stamping && g == 10) stamp[8 + c] = clock64();
+          };
+          // the two warps of a scheduler take the owed epilogue at different chunks: while one sits in its latencies the
+          // other keeps the MUFU busy
+          exp_step(0, va, vb);
+          if (g > 0 && hf == 0) epilogue(g - 1, pb, ph, pt);
+          exp_step(1, vb, va); exp_step(2, va, vb);
+          if (g > 0 && hf == 1) epilogue(g - 1, pb, ph, pt);
+          exp_step(3, vb, va); exp_step(4, va, vb);
+        }
         xch_sum[par * 256 + hf * 128 + r] = l;
         pb = b; ph = h; pt = t;
         if (timing) {
@@ -447,19 +530,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       epilogue(g - 1, pb, ph, pt);
     }
     tma_store_wait_all();  // the staging tile must outlive the bulk stores reading it
-  } else if (warp >= 4 + NUM_SOFTMAX_WARPS && n_tail > 0) {
+  } else if ((warp == 2 || warp == 3) && n_tail > 0) {
     // ---------------------------------------------------------------------------- tail queries (<= 8 rows)
     // Warp-level mma.sync.m16n8k16 on the K/V tiles already in shared memory (ldmatrix understands the TMA 128B
-    // swizzle: every 8x8 sub-matrix row is one 16-byte chunk).  Keys are dealt to the four warps in blocks of 16;
-    // the logit accumulators of two 8-key tiles are exactly the A fragment of the following P.V step, so P never
-    // leaves registers.  Only rows 0..7 of the 16-row fragments carry queries (rows 8..15 are ignored).
-    const int tw = warp - 4 - NUM_SOFTMAX_WARPS;   // 0..3
-    const int tt = tw * 32 + lane;                 // 0..127
+    // swizzle: every 8x8 sub-matrix row is one 16-byte chunk).  Keys are dealt to the two warps in blocks of 16.  The
+    // logits are computed twice (once for the row max, once for the exponentials) instead of being kept: 17 key blocks
+    // of accumulators would not fit the register budget this warpgroup is left with.  The logit accumulators of two
+    // 8-key tiles are exactly the A fragment of the following P.V step, so P never leaves registers.  Only rows 0..7
+    // of the 16-row fragments carry queries (rows 8..15 are ignored).
+    const int tw = warp - 2;                       // 0..1
+    const int tt = tw * 32 + lane;                 // 0..63
     const int nt = n_tail;
     const int g = lane >> 2, tq = lane & 3;        // fragment row group / thread-in-group
-    float* to = reinterpret_cast<float*>(smem + OFF_TO);       // [4 warps][8 rows][64]
-    float* tredm = reinterpret_cast<float*>(smem + OFF_TRED);  // [4][8]
-    float* treds = tredm + NUM_TAIL_WARPS * TAIL_MAX;          // [4][8]
+    float* to = reinterpret_cast<float*>(smem + OFF_TO);       // [2 warps][8 rows][64]
+    float* tredm = reinterpret_cast<float*>(smem + OFF_TRED);  // [2][8]
+    float* treds = tredm + NUM_TAIL_WARPS * TAIL_MAX;          // [2][8]
     const int nblk16 = tpad / 16;                // 16-key blocks, dealt round-robin to the warps
     int it = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
@@ -479,73 +564,72 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int chunk = 2 * ks + (lane >> 4);
         ldmatrix_x4(sTQ + row * ROW_BYTES + ((chunk ^ (row & 7)) << 4), qa[ks]);
       }
-      // ---- logits for this warp's key blocks: sacc[blk][tile][4]
-      constexpr int MAXB = 5;  // ceil(17 / 4)
-      float sacc[MAXB][2][4];
-      float mrow = -INFINITY;  // max over this thread's logits of row g (rows >= nt are ignored later)
-#pragma unroll
-      for (int bi = 0; bi < MAXB; ++bi) {
-        const int blk = tw + bi * NUM_TAIL_WARPS;
+      // logits of key block blk: sacc[tile][4], tile = 8-key half
+      auto block_logits = [&](int blk, float (&sacc)[2][4]) {
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sacc[bi][tile][e] = 0.f;
-        if (blk < nblk16) {
+          for (int e = 0; e < 4; ++e) sacc[tile][e] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            // B fragments (K^T): ldmatrix.x4 -> tile0 {b0,b1}, tile1 {b0,b1}; key row = blk*16 + tile*8 + (lane&7)
-            uint32_t kb[4];
-            const int key = blk * 16 + ((lane >> 4) << 3) + (lane & 7);
-            const int chunk = 2 * ks + ((lane >> 3) & 1);
-            ldmatrix_x4(sK + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), kb);
-            mma_bf16_16816(sacc[bi][0], qa[ks], kb[0], kb[1]);
-            mma_bf16_16816(sacc[bi][1], qa[ks], kb[2], kb[3]);
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          // B fragments (K^T): ldmatrix.x4 -> tile0 {b0,b1}, tile1 {b0,b1}; key row = blk*16 + tile*8 + (lane&7)
+          uint32_t kb[4];
+          const int key = blk * 16 + ((lane >> 4) << 3) + (lane & 7);
+          const int chunk = 2 * ks + ((lane >> 3) & 1);
+          ldmatrix_x4(sK + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), kb);
+          mma_bf16_16816(sacc[0], qa[ks], kb[0], kb[1]);
+          mma_bf16_16816(sacc[1], qa[ks], kb[2], kb[3]);
+        }
+      };
+      // ---- pass 1: row max over this warp's key blocks
+      float mrow = -INFINITY;  // max over this thread's logits of row g (rows >= nt are ignored later)
+#pragma unroll 1
+      for (int blk = tw; blk < nblk16; blk += NUM_TAIL_WARPS) {
+        float sacc[2][4];
+        block_logits(blk, sacc);
 #pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const int k0 = blk * 16 + tile * 8 + 2 * tq;  // keys of c0, c1
-            if (k0 < T) mrow = fmaxf(mrow, sacc[bi][tile][0]);
-            if (k0 + 1 < T) mrow = fmaxf(mrow, sacc[bi][tile][1]);
-          }
+        for (int tile = 0; tile < 2; ++tile) {
+          const int k0 = blk * 16 + tile * 8 + 2 * tq;  // keys of c0, c1
+          if (k0 < T) mrow = fmaxf(mrow, sacc[tile][0]);
+          if (k0 + 1 < T) mrow = fmaxf(mrow, sacc[tile][1]);
         }
       }
       mrow = fmaxf(mrow, __shfl_xor_sync(0xffffffffu, mrow, 1));
       mrow = fmaxf(mrow, __shfl_xor_sync(0xffffffffu, mrow, 2));
       if (tq == 0) tredm[tw * TAIL_MAX + g] = mrow;
       named_bar_sync(6, NUM_TAIL_WARPS * 32);
-      const float m = fmaxf(fmaxf(tredm[g], tredm[TAIL_MAX + g]), fmaxf(tredm[2 * TAIL_MAX + g], tredm[3 * TAIL_MAX + g]));
+      const float m = fmaxf(tredm[g], tredm[TAIL_MAX + g]);
       const float msl = m * p.sl2;
-      // ---- P = exp2(...), row sums, O partial = P V with P straight from the accumulator registers
+      // ---- pass 2: P = exp2(...), row sums, O partial = P V with P straight from the accumulator registers
       float oacc[8][4];
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd)
 #pragma unroll
         for (int e = 0; e < 4; ++e) oacc[nd][e] = 0.f;
       float lsum = 0.f;
+#pragma unroll 1
+      for (int blk = tw; blk < nblk16; blk += NUM_TAIL_WARPS) {
+        float sacc[2][4];
+        block_logits(blk, sacc);
+        uint32_t pa[4];
 #pragma unroll
-      for (int bi = 0; bi < MAXB; ++bi) {
-        const int blk = tw + bi * NUM_TAIL_WARPS;
-        if (blk < nblk16) {
-          uint32_t pa[4];
+        for (int tile = 0; tile < 2; ++tile) {
+          const int k0 = blk * 16 + tile * 8 + 2 * tq;
+          const float e0 = k0 < T ? ex2(fmaf(sacc[tile][0], p.sl2, -msl)) : 0.f;
+          const float e1 = k0 + 1 < T ? ex2(fmaf(sacc[tile][1], p.sl2, -msl)) : 0.f;
+          lsum += e0 + e1;
+          pa[2 * tile] = pack_bf16x2(e0, e1);   // rows g     (a0 / a2)
+          pa[2 * tile + 1] = 0u;                // rows g + 8 (a1 / a3): unused query rows
+        }
 #pragma unroll
-          for (int tile = 0; tile < 2; ++tile) {
-            const int k0 = blk * 16 + tile * 8 + 2 * tq;
-            const float e0 = k0 < T ? ex2(fmaf(sacc[bi][tile][0], p.sl2, -msl)) : 0.f;
-            const float e1 = k0 + 1 < T ? ex2(fmaf(sacc[bi][tile][1], p.sl2, -msl)) : 0.f;
-            lsum += e0 + e1;
-            pa[2 * tile] = pack_bf16x2(e0, e1);   // rows g     (a0 / a2)
-            pa[2 * tile + 1] = 0u;                // rows g + 8 (a1 / a3): unused query rows
-          }
-#pragma unroll
-          for (int nd2 = 0; nd2 < 4; ++nd2) {
-            // V as B operand (k = keys, n = dims): ldmatrix.x4.trans -> dims tile 2*nd2 {b0,b1}, tile 2*nd2+1 {b0,b1}
-            uint32_t vb[4];
-            const int key = blk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-            const int chunk = 2 * nd2 + (lane >> 4);
-            ldmatrix_x4_trans(sV + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), vb);
-            mma_bf16_16816(oacc[2 * nd2], pa, vb[0], vb[1]);
-            mma_bf16_16816(oacc[2 * nd2 + 1], pa, vb[2], vb[3]);
-          }
+        for (int nd2 = 0; nd2 < 4; ++nd2) {
+          // V as B operand (k = keys, n = dims): ldmatrix.x4.trans -> dims tile 2*nd2 {b0,b1}, tile 2*nd2+1 {b0,b1}
+          uint32_t vb[4];
+          const int key = blk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int chunk = 2 * nd2 + (lane >> 4);
+          ldmatrix_x4_trans(sV + key * ROW_BYTES + ((chunk ^ (key & 7)) << 4), vb);
+          mma_bf16_16816(oacc[2 * nd2], pa, vb[0], vb[1]);
+          mma_bf16_16816(oacc[2 * nd2 + 1], pa, vb[2], vb[3]);
         }
       }
       // K, V and the tail Q rows of this pair are no longer needed by these warps
@@ -566,7 +650,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float2 x = *reinterpret_cast<const float2*>(to + (w * TAIL_MAX + j) * HD + 2 * dp);
           acc.x += x.x; acc.y += x.y;
         }
-        const float l = (treds[j] + treds[TAIL_MAX + j]) + (treds[2 * TAIL_MAX + j] + treds[3 * TAIL_MAX + j]);
+        const float l = treds[j] + treds[TAIL_MAX + j];
         const float inv = 1.0f / l;
         const int tok = T - nt + j;
         *reinterpret_cast<uint32_t*>(p.out + (size_t(b) * T + tok) * (p.H * HD) + h * HD + 2 * dp) =
@@ -608,9 +692,10 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   const int grid = npairs < sm_count() ? npairs : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
   const bool special = T == 261 && !getenv("FP_ATTN_GENERIC");  // 224^2 crops: (224/14)^2 + 5 tokens
-  // POLY = 0: every exponential on the MUFU.  Moving 25-50 % of them to the FMA pipe (ex2_poly_x2) was measured and
-  // does not help: the softmax warps are bound by TMEM reads and latency, not by the 16-lane MUFU (0.297 ms with or
-  // without at B=521, T=261; 0.309 / 0.324 ms at 37.5 / 50 %).
+  // POLY = 0: every exponential on the MUFU.  Moving 25-50 % of them to the FMA pipe (ex2_poly_x2) was measured twice
+  // and is slower even now that the exponential pass sits at the MUFU floor (B=521, T=261: 0.283 ms without, 0.318 /
+  // 0.333 / 0.324 ms at 25 / 37.5 / 50 %): with two softmax warps per scheduler the longer dependent FMA chains cost
+  // more latency than the MUFU cycles they free.
 #define FP_LAUNCH_ATTN_POLY(TIMING_, TC_)                                                                            \
   do {                                                                                                               \
     auto kern = attention_kernel<TIMING_, TC_, 0u>;                                                                  \

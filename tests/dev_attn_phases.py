@@ -51,5 +51,5 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
-ms = timeit(lambda: ops.attention(qkv, B, T))
+ms = timeit(lambda: ops.attention(qkv, B, T), n=30)
 print(f"attention B={B} T={T}: {ms:.3f} ms  {4 * B * 16 * T * T * 64 / ms / 1e9:.1f} TFLOP/s")
