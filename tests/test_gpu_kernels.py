@@ -141,7 +141,8 @@ def test_attention(ops, B, T):
     check_stage(out, ref, f"attention B={B} T={T}", ulp_exact=False)
 
 
-@pytest.mark.parametrize("B,T", [(2, 905), (1, 273), (3, 512), (1, 529), (2, 1029), (1, 400)])
+@pytest.mark.parametrize("B,T", [(2, 905), (1, 273), (3, 512), (1, 529), (2, 1029), (1, 400),
+                                 (8, 400), (5, 700), (6, 1025)])    # several work items per CTA; a 16-key last block
 def test_attention_tiled_keys(ops, B, T):
     """Crops above 224^2 (905 tokens = the reference's 420^2 crops): key blocks of 256 with an online softmax."""
     from oracle.vit import contract_attention
