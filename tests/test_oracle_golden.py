@@ -231,3 +231,30 @@ def test_mip_chain_and_trimesh_adapters():
     vc = as_mesh(NS(vertices=np.zeros((3, 3)), faces=np.array([[0, 1, 2]]),
                     visual=NS(kind="vertex", vertex_colors=np.full((3, 4), 9, np.uint8))))
     assert vc.vertex_colors.shape == (3, 4) and vc.texture is None
+
+
+def test_raster_oracle_bilinear_texture_on_a_facing_quad():
+    """Independent float64 evaluation of the texture path (orientation v-up, REPEAT-free interior, bilinear on level 0
+    when magnified, x^2.2 after filtering, ambient 2, 1/2.2 gamma) on a quad parallel to the image plane."""
+    from freepose_b200.pipeline.utils import Mesh
+    from oracle import raster as R
+    rng = np.random.default_rng(5)
+    tex = rng.integers(0, 256, size=(24, 24, 3), dtype=np.uint8)
+    v = np.array([[-0.3, -0.3, 0.0], [0.3, -0.3, 0.0], [0.3, 0.3, 0.0], [-0.3, 0.3, 0.0]])
+    uv = np.stack([(v[:, 0] + 0.3) / 0.6, (0.3 - v[:, 1]) / 0.6], axis=1)       # top edge of the quad (y = -0.3) is v = 1
+    mesh = Mesh(v, np.array([[0, 1, 2], [0, 2, 3]]), None, uv, tex)
+    pose = np.eye(4)[None].copy()
+    pose[0, 2, 3] = 1.0
+    rgb, depth = R.render_mesh(mesh, pose, 320.0, 320.0, 112.0, 112.0, 224, msaa=1)
+    assert abs(float(depth[0, 100, 100]) - 1.0) < 1e-6 and depth[0, 5, 5] == 0
+    ys, xs = np.mgrid[24:200, 24:200]                                            # interior of the 192 px quad
+    X, Y = (xs + 0.5 - 112) / 320, (ys + 0.5 - 112) / 320
+    tx, ty = (X + 0.3) / 0.6 * 24 - 0.5, (Y + 0.3) / 0.6 * 24 - 0.5
+    x0, y0 = np.floor(tx).astype(int), np.floor(ty).astype(int)
+    fx, fy = (tx - x0)[..., None], (ty - y0)[..., None]
+    t = tex.astype(np.float64)
+    c = (t[y0, x0] * (1 - fx) + t[y0, x0 + 1] * fx) * (1 - fy) + (t[y0 + 1, x0] * (1 - fx) + t[y0 + 1, x0 + 1] * fx) * fy
+    want = np.floor(255 * np.minimum(1.0, 2 * (c / 255) ** 2.2) ** (1 / 2.2) + 0.5)
+    got = rgb[0, 24:200, 24:200].astype(np.float64)
+    assert np.abs(got - want).max() <= 1 and np.mean(got == want) > 0.97
+    assert got.std() > 20                                                        # a real image, not a constant
