@@ -70,7 +70,7 @@ struct Params {
   int n_tail;     // remainder query rows (<= 8) handled by the tail warps, 0 if none
   int nchunks;    // 64-key chunks
   float sl2;      // scale * log2(e)
-  long long* dbg;  // perf experiments: per-phase cycle counters of the tail warps (nullptr = off)
+  long long* dbg;  // perf experiments: per-phase cycle counters of softmax warp 4 of CTA 0 (nullptr = off)
 };
 
 using namespace attn;
@@ -239,7 +239,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (c < nchunks) {
             mbar_wait(&p_full[c], g & 1);
             tc_fence_after();
-            if (TIMING && p.dbg != nullptr && blockIdx.x == 0 && g == 10) p.dbg[16 + c] = clock64();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int key0 = c * 64 + k * 16;
@@ -256,10 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (has_next) {   // logits of the next tile for the key parts whose columns are now free
 #pragma unroll
               for (int i = 0; i < 3; ++i)
-                if (part_n[i] > 0 && c == part_last_chunk[i]) {
-                  issue_s(g + 1, nit, nt, i);
-                  if (TIMING && p.dbg != nullptr && blockIdx.x == 0 && g == 10) p.dbg[24 + i] = clock64();
-                }
+                if (part_n[i] > 0 && c == part_last_chunk[i]) issue_s(g + 1, nit, nt, i);
             }
           }
         }
@@ -274,8 +270,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     uint8_t* out_stage = smem + OFF_OST + (warp - 4) * 2048;  // 32 rows x 64 B, source of this warp's bulk stores
     const bool timing = TIMING && p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
-    const bool stamping = TIMING && p.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;   // warps 4 and 8
-    long long* stamp = p.dbg + 32 + hf * 16;
     long long tepi = 0;
 
     // Normalise and store tile gp (image b, head h, query tile t) from O[gp & 1].  Runs one tile late, between two
@@ -295,13 +289,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       mbar_wait(&o_full[ob], (gp >> 1) & 1);
       tc_fence_after();
-      if (timing) p.dbg[8] += clock64() - te0;
       uint32_t o[32];
       if (warp_active) {
         tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + ob * HD + hf * 32, o);
         tmem_ld_wait();
       }
-      if (timing) p.dbg[9] += clock64() - te0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
@@ -326,7 +318,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int jv = 0; jv < 4; ++jv) dst[jv] = w[jv];
         }
       }
-      if (timing) p.dbg[10] += clock64() - te0;
       if (full_rows) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -424,17 +415,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         } else {
           if (timing) { tk0 = clock64(); tepi = 0; }
-          if (stamping && g == 11) stamp[0] = clock64();
           mbar_wait(&s_full[0], par);
           tc_fence_after();
-          if (stamping && g == 11) stamp[1] = clock64();
           if (timing) tk1 = clock64();
           int parts_ready = 1;             // the key parts of S arrive on their own barriers, in order
           auto need_part = [&](int part) {
             while (parts_ready <= part) {
               mbar_wait(&s_full[parts_ready], par);
               tc_fence_after();
-              if (stamping && g == 11) stamp[1 + parts_ready] = clock64();
               ++parts_ready;
             }
           };
@@ -473,7 +461,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (kPrefetch && chunk_exists(0)) { issue_ld(0, va); tmem_ld_wait(); }
           max_step(0, va, vb); max_step(1, vb, va); max_step(2, va, vb); max_step(3, vb, va); max_step(4, va, vb);
           need_part(2);   // (every tile consumes one phase of all three barriers, whatever its chunk count)
-          if (stamping && g == 11) stamp[4] = clock64();
           if (timing) tk2 = clock64();
           if (kPrefetch && chunk_exists(0)) issue_ld(0, va);  // pass 2's first chunk travels during the max exchange
           // exchange buffers alternate with the tile parity: the partner warp may already be a phase ahead, and the
@@ -506,7 +493,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[c]);
-            if (stamping && g == 10) stamp[8 + c] = clock64();
           };
           // the two warps of a scheduler take the owed epilogue at different chunks: while one sits in its latencies the
           // other keeps the MUFU busy

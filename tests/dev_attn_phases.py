@@ -11,7 +11,7 @@ from freepose_b200 import ops  # noqa: E402
 B, T = 521, 261
 torch.manual_seed(0)
 qkv = torch.randn(B * T, 3072, device="cuda").to(torch.bfloat16)
-dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
 for _ in range(2):
     ops.attention(qkv, B, T)
 torch.cuda.synchronize()
@@ -26,16 +26,6 @@ print("softmax warp 4 of CTA 0, cycles per tile over", n, "tiles")
 for k, v in names.items():
     print(f"  {v:18s} {d[k] / n:8.1f}")
 print("  total              %8.1f" % (sum(d[k] for k in names) / n))
-print("  epilogue cumulative: waits %.1f, +O load %.1f, +scale/stage %.1f" % (d[8] / n, d[9] / n, d[10] / n))
-t0 = d[16]
-rel = lambda v: v - t0 if v else None
-print("timeline around tile 10 -> 11 of CTA 0 (cycles, relative to the MMA thread seeing p_full[0] of tile 10)")
-print("  MMA sees p_full[c] (tile 10):      ", [rel(v) for v in d[16:21]])
-print("  MMA issued part i of tile 11:      ", [rel(v) for v in d[24:27]])
-for hf in (0, 1):
-    s0 = 32 + 16 * hf
-    print(f"  warp hf={hf}: arrives p_full[c] (t10): ", [rel(v) for v in d[s0 + 8:s0 + 13]])
-    print(f"  warp hf={hf}: tile 11 start, parts A/B/C seen, pass1 end: ", [rel(v) for v in d[s0:s0 + 5]])
 
 
 def timeit(fn, n=10):
