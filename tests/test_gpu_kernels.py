@@ -371,6 +371,28 @@ def test_renderer_accepts_trimesh_like_inputs(ops):
     assert (depth > 0).sum() > 100 and set(np.unique(rgb[depth > 0])) <= {64, 128, 191, 255}   # white x MSAA coverage
 
 
+def test_raster_long_offscreen_triangles_with_small_clipped_boxes(ops):
+    """Triangles whose vertices are thousands of pixels apart but whose viewport-clipped box is a few pixels: they must not
+    take the 32-bit small-triangle path (their edge functions do not fit) -- bit-exact against the oracle."""
+    from freepose_b200.pipeline.utils import Mesh
+    from oracle import raster as R
+    px = lambda u, v, z=1.0: [(u - 112.0) / 320.0 * z, (v - 112.0) / 320.0 * z, z - 1.0]
+    verts = np.array([px(-4000, -4000), px(5, 2), px(-4000, 3),         # wedge into the top-left corner: clipped box 6 x 3 px
+                      px(4224, -4000), px(218, 2), px(4224, 3),         # ... and into the top-right corner
+                      px(100, 100), px(9000, 104), px(100, 108),        # long to the right, big on screen too
+                      px(50, 50, 1.2), px(52, 50, 1.2), px(51, 52, 1.2)])   # an ordinary tiny one
+    faces = np.arange(12).reshape(4, 3)
+    colors = np.tile(np.array([[90, 40, 20], [20, 90, 40], [40, 20, 90]], np.uint8), (4, 1))
+    m = Mesh(verts, faces, colors)
+    pose = np.eye(4)[None].copy()
+    pose[0, 2, 3] = 1.0
+    for msaa in (4, 1):
+        want_rgb, want_depth = R.render_mesh(m, pose, 320.0, 320.0, 112.0, 112.0, 224, msaa)
+        rgb, depth = ops.rasterize_mesh(m, torch.from_numpy(pose).float().to(dev), 320.0, 320.0, 112.0, 112.0, 224, msaa)
+        assert np.array_equal(rgb.cpu().numpy(), want_rgb) and np.array_equal(depth.cpu().numpy(), want_depth)
+        assert (want_depth[0, 0:3, 0:5] > 0).any() and (want_depth[0, 0:3, 219:224] > 0).any()
+
+
 def test_raster_behind_camera_and_empty(ops):
     from freepose_b200.pipeline.utils import mesh_to_device
     m = _mesh(1)
