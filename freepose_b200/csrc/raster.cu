@@ -434,27 +434,37 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   }
 }
 
-// MODE 0 / 1: triangles (key payload = face), 2: points (key payload = vertex, flat colour)
+// MODE 0 / 1: triangles (key payload = face), 2: points (key payload = vertex, flat colour).
+// One thread per pixel, a warp = 32 consecutive pixels of a view: covered pixels come in runs along a row, so warps are
+// mostly all-covered or all-background (the earlier 4-pixels-per-thread mapping spread a warp over 128 pixels and ran with
+// 12 of 32 lanes active).  Depth goes out as one coalesced float per lane; the 96 RGB bytes of a warp are assembled into 24
+// words with two shuffles per lane.
 template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
                const int* __restrict__ faces, const Surface sf, uint8_t* __restrict__ rgb, float* __restrict__ depth,
                int V, int res) {
   const int b = blockIdx.y;
-  const int quads_per_row = res >> 2;
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (qi >= quads_per_row * res) return;
-  const int py = qi / quads_per_row, px0 = (qi - py * quads_per_row) << 2;
+  const int npix = res * res;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp_base = p - lane;
+  if (warp_base >= npix) return;
+  const bool live = p < npix;
+  const int py = live ? p / res : 0, px = live ? p - py * res : 0;
   const ScreenVertex* svb = sv + size_t(b) * V;
-  const unsigned long long* kv = keys + (size_t(b) * res * res + size_t(py) * res + px0) * S;
-  uint8_t pix[12];
-  float dep[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  int acc[3] = {0, 0, 0};
+  float dep = 0.f;
+  if (live) {
+    const unsigned long long* kv = keys + (size_t(b) * npix + p) * S;
     unsigned long long k[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) k[s] = kv[i * S + s];
-    int acc[3] = {0, 0, 0};
+    if (S == 4) {
+      const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(kv);
+      const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(kv + 2);
+      k[0] = k01.x; k[1] = k01.y; k[2 % S] = k23.x; k[3 % S] = k23.y;
+    } else {
+      k[0] = kv[0];
+    }
     unsigned last_face = 0xffffffffu;
     int col[3] = {0, 0, 0};
 #pragma unroll
@@ -467,28 +477,28 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
             for (int ch = 0; ch < 3; ++ch)
               col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), sf.ambient_255), sf.gamma_lut);
           } else {
-            shade<MODE>(svb, faces, sf, face, px0 + i, py, col);
+            shade<MODE>(svb, faces, sf, face, px, py, col);
           }
           last_face = face;
         }
         acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2];
       }
     }
-    if (S == 4) {
-      pix[3 * i] = uint8_t((acc[0] + 2) >> 2);
-      pix[3 * i + 1] = uint8_t((acc[1] + 2) >> 2);
-      pix[3 * i + 2] = uint8_t((acc[2] + 2) >> 2);
-    } else {
-      pix[3 * i] = uint8_t(acc[0]); pix[3 * i + 1] = uint8_t(acc[1]); pix[3 * i + 2] = uint8_t(acc[2]);
-    }
-    dep[i] = (k[0] != ~0ull) ? __uint_as_float(unsigned(k[0] >> 32)) : 0.f;
+    if (S == 4) { acc[0] = (acc[0] + 2) >> 2; acc[1] = (acc[1] + 2) >> 2; acc[2] = (acc[2] + 2) >> 2; }
+    dep = (k[0] != ~0ull) ? __uint_as_float(unsigned(k[0] >> 32)) : 0.f;
+    depth[size_t(b) * npix + p] = dep;
   }
-  uint32_t* o = reinterpret_cast<uint32_t*>(rgb + (size_t(b) * res * res + size_t(py) * res + px0) * 3);
-  o[0] = pix[0] | (pix[1] << 8) | (pix[2] << 16) | (uint32_t(pix[3]) << 24);
-  o[1] = pix[4] | (pix[5] << 8) | (pix[6] << 16) | (uint32_t(pix[7]) << 24);
-  o[2] = pix[8] | (pix[9] << 8) | (pix[10] << 16) | (uint32_t(pix[11]) << 24);
-  *reinterpret_cast<float4*>(depth + size_t(b) * res * res + size_t(py) * res + px0) =
-      make_float4(dep[0], dep[1], dep[2], dep[3]);
+  const unsigned c24 = unsigned(acc[0]) | (unsigned(acc[1]) << 8) | (unsigned(acc[2]) << 16);
+  uint8_t* out = rgb + (size_t(b) * npix + warp_base) * 3;      // 4-byte aligned: npix and warp_base are multiples of 4
+  if (warp_base + 32 <= npix) {
+    // word w (0..23) holds bytes 4w..4w+3 = the tail of pixel a = 4w/3 and the head of pixel a+1
+    const int a = (4 * lane) / 3, o = (4 * lane) - 3 * a;
+    const unsigned ca = __shfl_sync(0xffffffffu, c24, a & 31);
+    const unsigned cb = __shfl_sync(0xffffffffu, c24, (a + 1) & 31);
+    if (lane < 24) reinterpret_cast<uint32_t*>(out)[lane] = (ca >> (8 * o)) | (cb << (24 - 8 * o));
+  } else if (live) {
+    out[3 * lane] = uint8_t(acc[0]); out[3 * lane + 1] = uint8_t(acc[1]); out[3 * lane + 2] = uint8_t(acc[2]);
+  }
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -501,7 +511,7 @@ int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* key
   sf.ambient_255 = sf.ambient / 255.0f;
   sf.colors = a.colors; sf.uv = a.uv; sf.texture = a.texture; sf.srgb_lut = a.srgb_lut; sf.gamma_lut = a.gamma_lut;
   sf.tex_w = a.tex_w; sf.tex_h = a.tex_h; sf.tex_levels = a.tex_levels;
-  const dim3 rgrid((a.res * a.res / 4 + 255) / 256, a.B);
+  const dim3 rgrid((a.res * a.res + 255) / 256, a.B);
   if (a.primitive == 1) {
     point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res, znear, zfar);
     FP_CUDA(cudaGetLastError());
