@@ -21,8 +21,8 @@
 // trimesh.PointCloud inputs (renderer.py:46-51) are GL points of size 1: a one-pixel square sprite centred on the
 // projected vertex, flat vertex colour, the vertex's own depth.
 //
-// Kernels: clear keys -> vertex transform -> triangle (warp-cooperative for large triangles) or point scatter ->
-// resolve (4 pixels per thread, 12-byte RGB + 16-byte depth vector stores).
+// Kernels: clear keys -> vertex transform -> triangle (32-bit edge functions for small triangles, warp-cooperative walk
+// for large ones) or point scatter -> resolve (one thread per pixel; coalesced depth, shuffle-assembled RGB words).
 #include "common.cuh"
 #include "kernels.h"
 
