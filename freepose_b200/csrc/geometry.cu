@@ -135,6 +135,17 @@ __device__ __forceinline__ bool crop_source(const CropParams& c, int Y, int X, i
   return true;
 }
 
+// One axis of crop_source: output coordinate `o` -> source coordinate along that axis; false for padding.
+__device__ __forceinline__ bool crop_source_axis(const CropParams& c, int o, int pad, int size1, int size0, int origin,
+                                                 int& src) {
+  int m = o;
+  if (!c.padded) m = nearest_src(o, c.inv2, c.s2);
+  const int t = m - pad;
+  if (t < 0 || t >= size1) return false;
+  src = origin + nearest_src(t, c.inv1, size0);
+  return true;
+}
+
 // SRC_U8: source is u8 HWC (a render); else fp32 CHW.  DST_PATCH: write the normalised bf16 patch matrix;
 // else the fp32 CHW crop in [0,1].
 template <bool SRC_U8, bool DST_PATCH>
@@ -156,24 +167,43 @@ crop_kernel(const void* __restrict__ src, const int32_t* __restrict__ boxes, int
   const CropParams c = cp;
   const int g = T / 14;
   if (DST_PATCH) {
+    // The composed crop is separable (source row depends on the output row only, source column on the output column
+    // only): tabulate both maps once per CTA, then every thread gathers 8 consecutive matrix columns and writes 16 bytes.
+    __shared__ short map_y[1024], map_x[1024];
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      int ty, tx;
+      map_y[i] = (c.ok && crop_source_axis(c, i, c.pad_top, c.h1, c.h0, c.y1, ty)) ? short(ty) : short(-1);
+      map_x[i] = (c.ok && crop_source_axis(c, i, c.pad_left, c.w1, c.w0, c.x1, tx)) ? short(tx) : short(-1);
+    }
+    __syncthreads();
     bf16* out = reinterpret_cast<bf16*>(dst) + size_t(b) * g * g * Kpad;
-    const int total = g * g * Kpad;
+    const int groups_per_row = Kpad / 8;
+    const int total = g * g * groups_per_row;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(src) + size_t(b) * src_h * src_w * 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      const int col = i % Kpad, row = i / Kpad;
-      bf16 v = __float2bfloat16_rn(0.f);
-      if (col < 588) {
-        const int ch = col / 196, rem = col - ch * 196;
-        const int ky = rem / 14, kx = rem - ky * 14;
-        const int py = row / g, px = row - py * g;
-        const int Y = py * 14 + ky, X = px * 14 + kx;
-        int sy, sx, val = 0;
-        if (c.ok && crop_source(c, Y, X, sy, sx)) {
-          if (SRC_U8)
-            val = reinterpret_cast<const uint8_t*>(src)[((size_t(b) * src_h + sy) * src_w + sx) * 3 + ch];
+      const int row = i / groups_per_row, col0 = (i - row * groups_per_row) * 8;
+      const int py = row / g, px = row - py * g;
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t pair = 0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int col = col0 + j + h2;
+          bf16 v = __float2bfloat16_rn(0.f);
+          if (col < 588) {
+            const int ch = col / 196, rem = col - ch * 196;
+            const int ky = rem / 14, kx = rem - ky * 14;
+            const int sy = map_y[py * 14 + ky], sx = map_x[px * 14 + kx];
+            int val = 0;
+            if (SRC_U8 && sy >= 0 && sx >= 0) val = img[(size_t(sy) * src_w + sx) * 3 + ch];
+            v = norm_lut[ch * 256 + val];
+          }
+          pair |= uint32_t(*reinterpret_cast<const uint16_t*>(&v)) << (16 * h2);
         }
-        v = norm_lut[ch * 256 + val];
+        w[j >> 1] = pair;
       }
-      out[i] = v;
+      *reinterpret_cast<uint4*>(out + size_t(row) * Kpad + col0) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   } else {
     float* out = reinterpret_cast<float*>(dst) + size_t(b) * 3 * T * T;
@@ -271,6 +301,7 @@ int crop_resize_pad(const void* src, int src_is_u8_hwc, const int32_t* boxes, co
   FP_REQUIRE(!dst_is_patches || (norm_lut != nullptr && src_is_u8_hwc),
              "crop: the patch-matrix output needs a u8 source and the normalisation LUT");
   FP_REQUIRE(B <= 65535, "crop: at most 65535 images per call");
+  FP_REQUIRE(!dst_is_patches || T <= 1024, "crop: patch-matrix targets above 1024 px are not supported");
   if (B <= 0) return 0;
   const int g = T / 14;
   const int total = dst_is_patches ? g * g * Kpad : 3 * T * T;
