@@ -111,15 +111,11 @@ class TrackingRefiner:
     def _get_threshold_for_confidence(self, similarity_matrices, top_quantile=0.2):
         """tracking_refiner.py:59-68: lower edge of the histogram bin (50 bins over the positive similarities) at which
         the count accumulated from the top exceeds ``top_quantile`` of all positive entries."""
-        counts, values = np.histogram(similarity_matrices[similarity_matrices > 0], bins=50)
-        cutoff_value = counts.sum() * top_quantile
-        cum_ = 0
-        v = values[0]
-        for c, v in zip(counts[::-1], values[:-1][::-1]):
-            cum_ += c
-            if cum_ > cutoff_value:
-                break
-        return v
+        counts, edges = np.histogram(similarity_matrices[similarity_matrices > 0], bins=50)
+        from_top = np.cumsum(counts[::-1])
+        over = from_top > counts.sum() * top_quantile
+        k = int(np.argmax(over)) if over.any() else len(counts) - 1     # the reference's loop falls through to bin 0
+        return edges[:-1][::-1][k]
 
     def pose_confidence(self, mesh, photo, K, transform):
         return self.pose_confidences(mesh, [photo], K, [transform])[0].cpu().numpy()
