@@ -119,6 +119,8 @@ class WebTemplateDataset(torch.utils.data.Dataset):
         self.crop = crop
         self.n_views = n_views
         self.frame_index = self.frame_index.str.replace("_", "")
+        self._index = {}     # shard path -> {member name: (data offset, size)}; the reference pickles a TarInfo dict beside
+                             # every shard (template.py:54-61), here the index lives in memory for the process lifetime
 
     def __len__(self):
         return len(self.frame_index)
@@ -133,11 +135,21 @@ class WebTemplateDataset(torch.utils.data.Dataset):
         tar_path = self.wds_dir / f"shard-{idx // MESHES_PER_SHARD:06d}.tar"
         model_name = self.frame_index[idx].replace("_", "")
         rgbs, depths = [], []
-        with tarfile.open(tar_path.as_posix()) as tar:
-            members = {m.name: m for m in tar.getmembers()}
+        key = tar_path.as_posix()
+        if key not in self._index:
+            with tarfile.open(key) as tar:
+                self._index[key] = {m.name: (m.offset_data, m.size) for m in tar.getmembers()}
+        members = self._index[key]
+
+        def member(f, name):
+            off, size = members[name]
+            f.seek(off)
+            return io.BytesIO(f.read(size))
+
+        with open(key, "rb") as f:
             for k in range(self.n_views):
-                rgb = Image.open(io.BytesIO(tar.extractfile(members[f"{model_name}_{k}.rgb.png"]).read()))
-                dep = Image.open(io.BytesIO(tar.extractfile(members[f"{model_name}_{k}.depth.png"]).read()))
+                rgb = Image.open(member(f, f"{model_name}_{k}.rgb.png"))
+                dep = Image.open(member(f, f"{model_name}_{k}.depth.png"))
                 rgbs.append(np.array(rgb.convert("RGB")))
                 depths.append(np.array(dep))
         return rgbs, depths, model_name, tar_path.name
