@@ -81,6 +81,10 @@ SIGNATURES = {
     "fp_roi_align": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "fp_depth_mask_cubic": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "fp_patch_cosine": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "fp_comm_unique_id": (_i, [_vp]),
+    "fp_comm_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "fp_allgather_scores": (_i, [_vp, _vp, _i, _vp]),
+    "fp_comm_destroy": (_i, [_vp]),
 }
 
 _lib = None
@@ -120,7 +124,23 @@ def ptr(t: torch.Tensor | None):
         raise RuntimeError("freepose_b200 kernels take CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("freepose_b200 kernels take contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on torch.cuda.current_stream(): a tensor of another GPU would be dereferenced on the wrong device
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "wrap the call in `with torch.cuda.device(tensor.device)`")
     return t.data_ptr()
+
+
+def on_device(method):
+    """Decorator for methods of objects with a ``.device``: runs the call with that GPU current, so streams, launches
+    and per-device kernel attributes all refer to the device the object's tensors live on."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
 
 
 def stream_ptr() -> int:

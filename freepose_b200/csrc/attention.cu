@@ -685,7 +685,7 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
 #define FP_LAUNCH_ATTN_POLY(TIMING_, TC_)                                                                            \
   do {                                                                                                               \
     auto kern = attention_kernel<TIMING_, TC_, 0u>;                                                                  \
-    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                    \
+    FP_ENSURE_DYN_SMEM(kern, SMEM_BYTES);                                                                            \
     kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmQt, tmKV, tmOut, p);                                      \
   } while (0)
   if (p.dbg && special) FP_LAUNCH_ATTN_POLY(true, 261);

@@ -419,11 +419,7 @@ int attention_long_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float s
   p.nq = (T + QT - 1) / QT;
   p.nkb = (tpad + KB - 1) / KB;
   p.sl2 = scale * 1.4426950408889634f;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  FP_ENSURE_DYN_SMEM(attention_long_kernel, SMEM_BYTES);
   const long long nitems = (long long)B * H * p.nq;
   const int grid = nitems < sm_count() ? int(nitems) : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);

@@ -171,4 +171,13 @@ FP_API int fp_patch_cosine(const void* feats_a, const void* feats_b, const uint8
   return fp::patch_cosine(B16(feats_a), B16(feats_b), mask, rows, dim, out, S(stream));
 }
 
+FP_API int fp_comm_unique_id(fp_comm_id* id) { return fp::comm_unique_id(id); }
+FP_API int fp_comm_create(const fp_comm_id* id, int rank, int world, void** comm) {
+  return fp::comm_create(id, rank, world, comm);
+}
+FP_API int fp_allgather_scores(void* comm, float* scores, int per_rank, void* stream) {
+  return fp::comm_allgather_scores(comm, scores, per_rank, S(stream));
+}
+FP_API int fp_comm_destroy(void* comm) { return fp::comm_destroy(comm); }
+
 }  // extern "C"

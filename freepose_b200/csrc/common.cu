@@ -28,13 +28,32 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> cache[64];   // per device ordinal (0 = not queried yet)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   return n;
+}
+
+static std::mutex g_smem_mu;
+bool dyn_smem_needed(DynSmemOnce& once, int* device) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  *device = dev;
+  if (dev < 0 || dev >= 64) return true;
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  return !((once.mask >> dev) & 1ull);
+}
+void dyn_smem_done(DynSmemOnce& once, int device) {
+  if (device < 0 || device >= 64) return;
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  once.mask |= 1ull << device;
 }
 
 // ---------------------------------------------------------------------------------------------- profiler

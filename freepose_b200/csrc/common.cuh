@@ -31,7 +31,22 @@ int cuda_fail(cudaError_t e, const char* what);
     }                               \
   } while (0)
 
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function setting: one of these per launch site
+// remembers on which devices it has been applied (bit = device ordinal; ordinals >= 64 always re-apply).
+struct DynSmemOnce { unsigned long long mask = 0; };
+bool dyn_smem_needed(DynSmemOnce& once, int* device);
+void dyn_smem_done(DynSmemOnce& once, int device);
+#define FP_ENSURE_DYN_SMEM(func, bytes)                                                              \
+  do {                                                                                               \
+    static fp::DynSmemOnce _once;                                                                    \
+    int _dev = 0;                                                                                    \
+    if (fp::dyn_smem_needed(_once, &_dev)) {                                                         \
+      FP_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));     \
+      fp::dyn_smem_done(_once, _dev);                                                                \
+    }                                                                                                \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // Launch accounting + optional CUDA-event timing per kernel family (bench.py's live roofline numbers).

@@ -525,11 +525,7 @@ static int prof_kind(int mode, int K) {
 template <int MODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
            cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  FP_ENSURE_DYN_SMEM(gemm_kernel<MODE>, SMEM_BYTES);
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
@@ -541,11 +537,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 template <int MODE>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
             cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_done = true;
-  }
+  FP_ENSURE_DYN_SMEM(gemm2_kernel<MODE>, SMEM2_BYTES);
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
   const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   ProfScope prof(prof_kind(MODE, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);

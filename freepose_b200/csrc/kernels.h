@@ -134,6 +134,13 @@ int patch_cosine(const bf16* a, const bf16* b, const uint8_t* mask, int rows, in
 
 // ---------------------------------------------------------------------------------------- ViT
 struct fp_vit_weights;
+struct fp_comm_id;
+namespace fp {
+int comm_unique_id(fp_comm_id* out);
+int comm_create(const fp_comm_id* id, int rank, int world, void** comm_out);
+int comm_allgather_scores(void* comm, float* scores, int per_rank, cudaStream_t stream);
+int comm_destroy(void* comm);
+}  // namespace fp
 namespace fp {
 size_t vit_workspace_bytes(int dim, int mlp_dim, int B, int res);
 int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int B, int res, int layer,

@@ -304,11 +304,7 @@ int retrieval_scan(const bf16* db, const bf16* queries, long long M, int D, int 
   FP_REQUIRE((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(queries) & 15) == 0,
              "retrieval_scan: pointers must be 16-byte aligned");
   if (M == 0 || Q == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FP_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_QUERIES * 1024 * 2));
-    attr_done = true;
-  }
+  FP_ENSURE_DYN_SMEM(scan_kernel, MAX_QUERIES * 1024 * 2);
   const long long want = (M + RT_WARPS - 1) / RT_WARPS;
   const int grid = int(want < (long long)sm_count() * 8 ? want : (long long)sm_count() * 8);
   for (int q0 = 0; q0 < Q; q0 += MAX_QUERIES) {  // the database is re-read once per 32 queries

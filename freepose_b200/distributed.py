@@ -39,14 +39,35 @@ def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
 
 class ScoreGather:
     """Owns the (world * per) fp32 gather buffer.  ``local_view(rank)`` is where this rank's score kernel writes
-    its scores directly, so no copy kernel runs between scoring and the collective."""
+    its scores directly, so no copy kernel runs between scoring and the collective.
 
-    def __init__(self, n_total: int, world: int, device):
+    On CUDA the collective is ``fp_allgather_scores`` of the C ABI (an NCCL communicator created by the library from
+    an id that rank 0 makes and torch.distributed hands round), enqueued on the current compute stream right behind the
+    score kernel.  On CPU tensors (gloo tests of the host logic) it is ``torch.distributed.all_gather_into_tensor``."""
+
+    def __init__(self, n_total: int, world: int, device, rank: int | None = None):
         self.n = n_total
         self.world = world
         self.per = -(-n_total // world)
+        self.device = torch.device(device)
         # padding slots (when world does not divide n) stay at -inf and never win the top-k
         self.buf = torch.full((world * self.per,), float("-inf"), dtype=torch.float32, device=device)
+        self._comm = None
+        if world > 1 and self.device.type == "cuda":
+            import ctypes as C
+            from . import _lib
+            lib = _lib.load()
+            rank = dist.get_rank() if rank is None else rank
+            ident = (C.c_char * 128)()
+            if rank == 0:
+                _lib.check(lib.fp_comm_unique_id(ident), "fp_comm_unique_id")
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (C.c_char * 128).from_buffer_copy(box[0])
+            comm = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.fp_comm_create(ident, rank, world, C.byref(comm)), "fp_comm_create")
+            self._comm, self._lib = comm, lib
 
     def local_view(self, rank: int) -> torch.Tensor:
         return self.buf[rank * self.per:(rank + 1) * self.per]
@@ -54,9 +75,18 @@ class ScoreGather:
     def gather(self, rank: int) -> torch.Tensor:
         """All ranks end with all scores; returns the first n_total entries (global hypothesis order)."""
         if self.world > 1:
-            dist.all_gather_into_tensor(self.buf, self.local_view(rank).clone() if self.buf.device.type == "cpu"
-                                        else self.local_view(rank))
+            if self._comm is not None:
+                from . import _lib
+                _lib.check(self._lib.fp_allgather_scores(self._comm, _lib.ptr(self.buf), self.per, _lib.stream_ptr()),
+                           "fp_allgather_scores")
+            else:
+                dist.all_gather_into_tensor(self.buf, self.local_view(rank).clone())
         return self.buf[:self.n]
+
+    def close(self):
+        if self._comm is not None:
+            self._lib.fp_comm_destroy(self._comm)
+            self._comm = None
 
 
 def stable_topk_host(scores: torch.Tensor, k: int):

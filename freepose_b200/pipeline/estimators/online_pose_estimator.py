@@ -7,6 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import ops
+from ..._lib import on_device
 from ..utils import as_mesh, rescaled_extents, tco_from_extents
 from .pose_estimator import DinoPoseEstimator
 
@@ -30,6 +31,7 @@ class DinoOnlinePoseEstimator(nn.Module):
         self.renderer = self.coarse_estimator.renderer
         self.rendering_scale = 0.25
         self.device = self.coarse_estimator.device
+        self._scaled_meshes = {}   # id(mesh) -> (mesh, mesh at rendering scale): uploaded / mip-mapped once, not per frame
 
     def to(self, *args, **kwargs):
         return self
@@ -52,7 +54,21 @@ class DinoOnlinePoseEstimator(nn.Module):
         return self.forward_fine(proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose,
                                  neighborhood, layer, mask_scores, query_feat)
 
+    def _scaled_mesh(self, mesh):
+        """The caller's mesh at rendering scale (the reference scales in place and back, online_pose_estimator.py:60,87).
+        Cached per mesh object so that the per-frame video loop neither copies the mesh nor re-uploads vertices,
+        faces and texture (the device copies hang off the scaled Mesh)."""
+        hit = self._scaled_meshes.get(id(mesh))
+        if hit is not None and hit[0] is mesh:
+            return hit[1]
+        scaled = as_mesh(mesh).copy().apply_scale(self.rendering_scale)
+        if len(self._scaled_meshes) >= 64:
+            self._scaled_meshes.pop(next(iter(self._scaled_meshes)))
+        self._scaled_meshes[id(mesh)] = (mesh, scaled)
+        return scaled
+
     @torch.inference_mode()
+    @on_device
     def forward_fine(self, proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose,
                      neighborhood=15, layer=22, mask_scores=False, query_feat=None):
         normalise_query = query_feat is None
@@ -63,7 +79,7 @@ class DinoOnlinePoseEstimator(nn.Module):
         if close.size == 0:
             raise ValueError("no fine pose within the neighbourhood of prev_pose")
         selected = self.fine_mesh_poses[close]
-        m = as_mesh(mesh).copy().apply_scale(self.rendering_scale)  # the reference scales in place and back
+        m = self._scaled_mesh(mesh)
         rgb, depth = self.renderer.render_device(m, selected)
         T = self.renderer.resolution
         patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True)

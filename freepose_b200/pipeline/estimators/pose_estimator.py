@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ..._lib import on_device
 from ..retrieval.dino import DINOv2FeatureExtractor
 from ..retrieval.renderer import MeshRenderer
 from ..utils import generate_poses, rescaled_extents, tco_from_extents
@@ -25,12 +26,18 @@ bf16 = torch.bfloat16
 
 class DinoPoseEstimator(nn.Module):
     def __init__(self, n_poses=600, cache_size=50, save_all=False, cache_dir="./data/cache", feature_extractor=None,
-                 resolution=420, **extractor_kwargs):
+                 resolution=420, device_cache_bytes=8 << 30, **extractor_kwargs):
         super().__init__()
         self.feature_extractor = feature_extractor or DINOv2FeatureExtractor(**extractor_kwargs)
         self.device = self.feature_extractor.engine.device
         self.mesh_poses = self.generate_poses(n_poses)
-        self.feature_cache = OrderedDict()  # model_name -> (n_views, P, 1024) bf16, device resident
+        # model_name -> (n_views, P, 1024) bf16 in (pinned) HOST memory, like the reference's CPU cache
+        # (pose_estimator.py:38-51): at the reference configuration one mesh is 600 x 900 x 1024 bf16 = 1.1 GB, so the
+        # default 50 entries would not fit next to the retrieval pool and the ViT workspace in HBM.
+        self.feature_cache = OrderedDict()
+        # the most recently used entries additionally stay resident on the device, capped by BYTES
+        self._device_cache = OrderedDict()
+        self.device_cache_bytes = int(device_cache_bytes)
         self.cache_size = cache_size
         self.save_all = save_all
         self.cache_dir = Path(cache_dir)
@@ -53,24 +60,49 @@ class DinoPoseEstimator(nn.Module):
                                                   out=feats[i:i + batch_size])
         return feats
 
+    def _to_host(self, features):
+        host = features.detach().to("cpu")
+        if torch.cuda.is_available() and not host.is_pinned():
+            host = host.pin_memory()      # async H2D on the next hit
+        return host
+
+    def _keep_on_device(self, key, features):
+        self._device_cache[key] = features
+        self._device_cache.move_to_end(key)
+        used = sum(t.numel() * t.element_size() for t in self._device_cache.values())
+        while used > self.device_cache_bytes and len(self._device_cache) > 1:
+            _, old = self._device_cache.popitem(last=False)
+            used -= old.numel() * old.element_size()
+        if used > self.device_cache_bytes:            # a single entry larger than the budget is not kept either
+            self._device_cache.clear()
+
     def _cache_features(self, key, features):
-        self.feature_cache[key] = features
+        """features: device tensor.  RAM LRU of `cache_size` entries; the evicted entry goes to disk (reference
+        pose_estimator.py:38-51)."""
+        self.feature_cache[key] = self._to_host(features)
         self.feature_cache.move_to_end(key)
+        self._keep_on_device(key, features)
         cache_path = self.cache_dir / f"{key}.pth"
         if self.save_all and not cache_path.exists():
             with open(cache_path, "wb") as f:
                 flock(f, LOCK_EX)
-                torch.save(features.cpu(), f)
+                torch.save(self.feature_cache[key], f)
                 flock(f, LOCK_UN)
         if len(self.feature_cache) > self.cache_size:
             oldest_key, oldest = self.feature_cache.popitem(last=False)
-            torch.save(oldest.cpu(), self.cache_dir / f"{oldest_key}.pth")
+            self._device_cache.pop(oldest_key, None)
+            torch.save(oldest, self.cache_dir / f"{oldest_key}.pth")
 
     def _get_template_features(self, template_dict, layer=22, batch_size=128):
         name = template_dict["model_name"]
         if name in self.feature_cache:
             self.feature_cache.move_to_end(name)
-            return self.feature_cache[name]
+            if name in self._device_cache:
+                self._device_cache.move_to_end(name)
+                return self._device_cache[name]
+            feats = self.feature_cache[name].to(self.device, non_blocking=True)
+            self._keep_on_device(name, feats)
+            return feats
         cache_path = self.cache_dir / f"{name}.pth"
         if cache_path.exists():
             feats = torch.load(cache_path).to(self.device, dtype=bf16)
@@ -87,6 +119,7 @@ class DinoPoseEstimator(nn.Module):
 
     # ---------------------------------------------------------------- reference contract
     @torch.inference_mode()
+    @on_device
     def forward(self, proposal, template_dict, K, bbox, est_scale, layer=22, batch_size=128,
                 return_query_feat=False):
         if self.cache_size > 0:
@@ -120,6 +153,7 @@ class DinoPoseEstimator(nn.Module):
 
     # ---------------------------------------------------------------- B200-native hot path
     @torch.inference_mode()
+    @on_device
     def render_features(self, mesh, poses=None, layer=22, resolution=None, query=None):
         """raster -> mask bbox -> CropResizePad -> patch matrix -> ViT.  Returns (feats (B,P,1024) bf16,
         depth (B,res,res) fp32, crop status[, query feats (1,P,1024)]).
@@ -142,15 +176,19 @@ class DinoPoseEstimator(nn.Module):
         return feats, depth, status
 
     @torch.inference_mode()
-    def forward_mesh(self, proposal, mesh, K, bbox, est_scale, layer=22, poses=None, k=3):
+    @on_device
+    def forward_mesh(self, proposal, mesh, K, bbox, est_scale, layer=22, poses=None, k=3, shard=None):
         """Render-and-compare of one proposal against all hypotheses of `mesh` (already at rendering scale).
-        Same outputs as ``forward`` (without 'retrieved_proposals')."""
+        Same outputs as ``forward`` (without 'retrieved_proposals').
+
+        ``shard = (rank, world, ScoreGather)``: hypothesis-sharded multi-GPU mode.  This rank
+        rasterises, embeds and scores only hypotheses ``shard_bounds(n, rank, world)``; the score kernel writes into
+        this rank's slice of the gather buffer, ONE all-gather makes every rank hold all n scores, and every rank then
+        runs the same deterministic top-k (ties -> lowest global index).  The k winning views are re-rasterised locally
+        for the translation (k renders instead of a second collective), so all ranks return identical results."""
         pose_list = self.mesh_poses if poses is None else list(poses)
-        feats, depth, _, query_feat = self.render_features(mesh, poses, layer=layer, query=proposal)
-        scores, top_idx, top_val, _ = ops.score_topk(feats, query_feat, k=k)
-        r = self.renderer.resolution
-        K_t = np.array([[self.renderer.focal, 0, r / 2], [0, self.renderer.focal, r / 2], [0, 0, 1]])
-        ext = ops.depth_extents(depth, K_t, view_idx=top_idx).cpu().numpy()
+        scores, top_idx, top_val, ext = self.forward_mesh_device(proposal, mesh, layer=layer, poses=poses, k=k, shard=shard)
+        ext = ext.cpu().numpy()
         top_indices = top_idx.cpu().numpy().astype(np.int64)
         out = {"TCO": [], "scores": top_val.cpu().numpy().astype(np.float32), "proposal": proposal, "K": K,
                "bbox": bbox, "all_scores": scores, "top_indices": top_indices}
@@ -158,3 +196,31 @@ class DinoPoseEstimator(nn.Module):
             dx, dy = rescaled_extents(ext[j], est_scale, recentre=True)
             out["TCO"].append(tco_from_extents(bbox, dx, dy, K, pose_list[idx]))
         return out
+
+    @torch.inference_mode()
+    @on_device
+    def forward_mesh_device(self, proposal, mesh, layer=22, poses=None, k=3, shard=None):
+        """The device part of ``forward_mesh``: enqueues everything on the current stream and returns device tensors
+        (all scores (n,) fp32, top-k indices int32, top-k scores fp32, depth extents (k,8) fp64) without any
+        device->host synchronisation."""
+        r = self.renderer.resolution
+        K_t = np.array([[self.renderer.focal, 0, r / 2], [0, self.renderer.focal, r / 2], [0, 0, 1]])
+        if shard is None:
+            feats, depth, _, query_feat = self.render_features(mesh, poses, layer=layer, query=proposal)
+            scores, top_idx, top_val, _ = ops.score_topk(feats, query_feat, k=k)
+            return scores, top_idx, top_val, ops.depth_extents(depth, K_t, view_idx=top_idx)
+        from ...distributed import shard_bounds
+        rank, world, sg = shard
+        P_all = self.renderer.poses_device(poses)
+        n = P_all.shape[0]
+        assert sg.n == n and sg.world == world, "gather buffer does not match the hypothesis count"
+        lo, hi = shard_bounds(n, rank, world)
+        if hi > lo:
+            feats, _, _, query_feat = self.render_features(mesh, P_all[lo:hi], layer=layer, query=proposal)
+            ops.score_topk(feats, query_feat, k=0, scores_out=sg.local_view(rank))
+        scores = sg.gather(rank)
+        top_idx, top_val = ops.topk(scores, k)
+        # winners' depth maps for the translation: the k winning poses are gathered ON THE DEVICE and re-rasterised on
+        # every rank (k renders instead of a second collective; no host round trip)
+        _, depth = self.renderer.render_device(mesh, P_all[top_idx.long()])
+        return scores, top_idx, top_val, ops.depth_extents(depth, K_t)

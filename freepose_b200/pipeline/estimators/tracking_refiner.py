@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from ... import ops
+from ..._lib import on_device
 from ...vit_engine import ViTEngine
 from ...vit_weights import VITB14_REG, load_state_dict_file, synthetic_state_dict
 from .. import refiner_utils
@@ -32,6 +33,7 @@ class TrackingRefiner:
         if not torch.cuda.is_available() or torch.device(dino_device).type != "cuda":
             raise RuntimeError("TrackingRefiner needs a CUDA device (no CPU fallback)")
         self.dino_device = torch.device(dino_device)
+        self.device = self.dino_device
         self.cotracker_device = cotracker_device
         if weights is None:
             import warnings
@@ -77,6 +79,7 @@ class TrackingRefiner:
         t = t.permute(2, 0, 1).contiguous()
         return t.float().div(255) if arr.dtype == np.uint8 else t.float()
 
+    @on_device
     def pose_confidences(self, mesh, frames, K, transforms) -> torch.Tensor:
         """All frames in one batch: (n,37,37) fp32 on the device (row i = reference pose_confidence(mesh, frames[i], K,
         transforms[i]))."""
@@ -97,12 +100,14 @@ class TrackingRefiner:
         return ops.patch_cosine(f_photo, f_render, mask.reshape(n, g * g)).view(n, g, g)
 
     # ------------------------------------------------------------------ reference-shaped API
+    @on_device
     def _render(self, mesh, width, height, K, transform):
         assert width == self.image_size and height == self.image_size
         rgb, depth = self._render_device(mesh, torch.from_numpy(np.asarray(K, dtype=np.float64)).view(1, 3, 3).float(),
                                          torch.from_numpy(np.asarray(transform, dtype=np.float64)).view(1, 4, 4).float())
         return rgb[0, :height, :width].cpu().numpy(), depth[0, :height, :width].cpu().numpy()
 
+    @on_device
     def _crop_image(self, mesh, image, K, transform):
         boxes, new_K, _ = self._crop_boxes(mesh, K, np.asarray(transform)[None])
         crop = ops.roi_align(self._to_image_tensor(image), boxes.to(self.dino_device), self.image_size, self.image_size, 2)
@@ -117,6 +122,7 @@ class TrackingRefiner:
         k = int(np.argmax(over)) if over.any() else len(counts) - 1     # the reference's loop falls through to bin 0
         return edges[:-1][::-1][k]
 
+    @on_device
     def pose_confidence(self, mesh, photo, K, transform):
         return self.pose_confidences(mesh, [photo], K, [transform])[0].cpu().numpy()
 

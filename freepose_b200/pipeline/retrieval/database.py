@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from ... import ops
+from ..._lib import on_device
 
 COARSE_K = 100  # extract_proposals_ground.py:140
 
@@ -114,6 +115,7 @@ class RetrievalDatabase:
             self._append(m, views)
 
     # ------------------------------------------------------------------ queries
+    @on_device
     def normalize(self, feats: torch.Tensor) -> torch.Tensor:
         """``F.normalize(feats, dim=-1)`` on a bf16 (or fp32 -> bf16) feature matrix (``extract_proposals_ground.py:121,134``)."""
         f = feats.to(self.device)
@@ -122,10 +124,12 @@ class RetrievalDatabase:
         f = f if f.dtype in (torch.float32, torch.bfloat16) else f.float()
         return ops.normalize_rows(f.contiguous())
 
+    @on_device
     def scores(self, features: torch.Tensor) -> torch.Tensor:
         """``(retrieval_features @ feature).float()`` for every row of ``features`` (Q, D) -> (Q, M) fp32."""
         return ops.retrieval_scan(self.features, features.contiguous())
 
+    @on_device
     def coarse(self, features: torch.Tensor, k: int = COARSE_K):
         """-> (scores (Q,k) fp32 descending, mesh indices (Q,k) int32)."""
         if k > self.M:
@@ -133,6 +137,7 @@ class RetrievalDatabase:
         idx, val = ops.topk_rows(self.scores(features), k)
         return val, idx
 
+    @on_device
     def fine(self, features: torch.Tensor, cand: torch.Tensor, topk: int) -> torch.Tensor:
         """Per candidate: ``torch.topk(views @ feature, topk).values.mean()`` -> (Q, C) fp32."""
         cand_host = cand.cpu().numpy()
@@ -143,6 +148,7 @@ class RetrievalDatabase:
         return ops.retrieval_fine(self._pool, self._start, self._count, int(self._count_host.max()), cand.contiguous(),
                                   features.contiguous(), topk)
 
+    @on_device
     def retrieve(self, features: torch.Tensor, topk: int = 0, coarse_k: int = COARSE_K, return_sparse: bool = False):
         """The per-proposal loop of ``extract_proposals_ground.py:136-160`` for all proposals at once.
 

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from ... import ops
+from ..._lib import on_device
 from ..bbox_utils import CropResizePad
 from ..utils import Mesh, as_mesh, generate_poses, mask_to_bbox, mesh_to_device
 
@@ -27,19 +28,27 @@ class MeshRenderer:
         self._poses_dev = None
 
     # ------------------------------------------------------------------ device path
+    @on_device
     def render_device(self, mesh, poses=None, cull_faces=False):
         """-> rgb u8 (B,res,res,3), depth fp32 (B,res,res) CUDA tensors."""
         m = as_mesh(mesh)
-        if poses is None:
-            if self._poses_dev is None:
-                self._poses_dev = torch.from_numpy(np.array(self.mesh_poses)).to(self.device, torch.float32)
-            P = self._poses_dev
-        else:
-            P = torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device)
+        P = self.poses_device(poses)
         r = self.resolution
         return ops.rasterize_mesh(m, P, self.focal, self.focal, r / 2, r / 2, r, msaa=self.msaa,
                                   cull_backfaces=cull_faces)
 
+    def poses_device(self, poses=None) -> torch.Tensor:
+        """(B,4,4) fp32 on the device: the renderer's own hypothesis set (uploaded once), a list / array of 4x4
+        matrices, or a device tensor passed through."""
+        if poses is None:
+            if self._poses_dev is None:
+                self._poses_dev = torch.from_numpy(np.array(self.mesh_poses)).to(self.device, torch.float32)
+            return self._poses_dev
+        if torch.is_tensor(poses):
+            return poses.to(self.device, torch.float32)
+        return torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device)
+
+    @on_device
     def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None):
         """Device version of generate_proposals: mask -> bbox -> CropResizePad.  Returns
         (patch matrix | fp32 crops, bbox (B,4) int32, masks u8 (B,res,res))."""

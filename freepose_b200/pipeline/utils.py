@@ -148,15 +148,16 @@ def mesh_to_device(mesh: Mesh, device):
         if mesh.faces is None:
             f = torch.zeros((0, 3), dtype=torch.int32, device=device)
         else:
-            f = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.faces, dtype=np.int32))).to(device)
+            f_host = np.ascontiguousarray(np.asarray(mesh.faces, dtype=np.int32))
+            if f_host.size and (f_host.min() < 0 or f_host.max() >= v.shape[0]):   # validated once, on the host
+                raise ValueError("mesh faces index outside the vertex array")
+            f = torch.from_numpy(f_host).to(device)
         if mesh.vertex_colors is not None:
             c = torch.from_numpy(np.ascontiguousarray(np.asarray(mesh.vertex_colors)[:, :3].astype(np.uint8))).to(device)
         elif mesh.texture is not None and mesh.uv is not None:
             c = None
         else:
             c = torch.full((v.shape[0], 3), 255, dtype=torch.uint8, device=device)
-        if f.numel() and (int(f.min()) < 0 or int(f.max()) >= v.shape[0]):
-            raise ValueError("mesh faces index outside the vertex array")
         mesh._device_cache[key] = (v, f, c)
     return mesh._device_cache[key]
 

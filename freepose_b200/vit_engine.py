@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 from ._lib import (FP_FEATURE_ALL, FP_FEATURE_CLS, FP_FEATURE_PATCH, FP_FEATURE_REG, FP_INPUT_IMAGE_BF16,
-                   FP_INPUT_IMAGE_F32, FP_INPUT_PATCHES, KPAD, check, load, ptr, stream_ptr)
+                   FP_INPUT_IMAGE_F32, FP_INPUT_PATCHES, KPAD, check, load, on_device, ptr, stream_ptr)
 from .vit_weights import VITL14_REG, VitConfig, interpolated_pos_embed, state_dict_depth
 
 bf16 = torch.bfloat16
@@ -94,6 +94,7 @@ class ViTEngine:
         g = res // self.cfg.patch_size
         return {"all": g * g + 5, "cls": 1, "reg": 4, "patch": g * g}[feature_type]
 
+    @on_device
     def forward(self, x: torch.Tensor, layer: int = 22, feature_type: str = "patch", res: int | None = None,
                 out: torch.Tensor | None = None) -> torch.Tensor:
         """x: (B,3,res,res) fp32 in [0,1] (Normalize applied on device), (B,3,res,res) bf16 already normalised,

@@ -237,6 +237,22 @@ FP_API int fp_depth_mask_cubic(const float* depth, int B, int res, int src_strid
 FP_API int fp_patch_cosine(const void* feats_a, const void* feats_b, const uint8_t* mask, int rows, int dim, float* out,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU; the hypotheses of a proposal are split contiguously over the
+ * ranks and the ONLY exchange is an all-gather of the per-hypothesis fp32 scores, after which every rank runs the same
+ * deterministic fp_topk.  No reference counterpart: the reference scales with SLURM array jobs + CSV concatenation
+ * (scripts/dino_inference.py:37-40, scripts/merge_results.py:14-29).
+ * NCCL is resolved with dlopen at the first call (the libnccl.so.2 PyTorch ships); the id is 128 opaque bytes made
+ * by rank 0 and handed to the other ranks by the host (torch.distributed / MPI / a file).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct fp_comm_id { char bytes[128]; } fp_comm_id;
+FP_API int fp_comm_unique_id(fp_comm_id* id /* host out */);
+FP_API int fp_comm_create(const fp_comm_id* id /* host */, int rank, int world, void** comm /* host out */);
+/* scores: (world * per_rank) fp32 on the device; this rank's slice [rank*per_rank, +per_rank) was written by
+ * fp_score_topk (scores_out pointing into the buffer).  In-place all-gather enqueued on `stream`. */
+FP_API int fp_allgather_scores(void* comm, float* scores, int per_rank, void* stream);
+FP_API int fp_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

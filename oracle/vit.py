@@ -40,9 +40,30 @@ import torch.nn.functional as F
 from freepose_b200.vit_weights import VITL14_REG, VitConfig, interpolated_pos_embed, state_dict_depth
 
 
+# Accumulation dtype of the contract mode.  float32 is the contract; float64 exists only so that a test can measure how
+# far two realisations of the SAME rounding contract drift apart through accumulation order alone
+# (tests/test_oracle_vit.py::test_contract_drift_fp32_vs_fp64_accumulation).
+ACC_DTYPE = torch.float32
+
+
+class accumulate_in:
+    """``with accumulate_in(torch.float64): ...`` -- contract-mode math in that dtype (rounding points unchanged)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global ACC_DTYPE
+        self.prev, ACC_DTYPE = ACC_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global ACC_DTYPE
+        ACC_DTYPE = self.prev
+
+
 def rb(x: torch.Tensor) -> torch.Tensor:
-    """Round an fp32 tensor to the nearest bf16 value (ties to even) and return it as fp32."""
-    return x.to(torch.bfloat16).to(torch.float32)
+    """Round to the nearest bf16 value (ties to even) and return it in the accumulation dtype (fp32)."""
+    return x.to(torch.bfloat16).to(ACC_DTYPE)
 
 
 class _LayerScale(nn.Module):
@@ -103,7 +124,7 @@ class _Block(nn.Module):
     # ---- explicit rounding contract (fp32 tensors holding bf16 values) -------------------
     def _forward_contract(self, x):
         cfg = self.cfg
-        f = lambda p: p.detach().float()
+        f = lambda p: p.detach().to(ACC_DTYPE)
         B, N, D = x.shape
         Hn, hd = cfg.num_heads, cfg.head_dim
         h = contract_layernorm(x, f(self.norm1.weight), f(self.norm1.bias), cfg.ln_eps)
@@ -215,8 +236,8 @@ class OracleViT(nn.Module):
     def _prepare_contract(self, x):
         """x: normalised image, bf16 values (any float dtype).  Returns fp32 holding bf16 values."""
         B, nc, w, h = x.shape
-        f = lambda p: p.detach().float()
-        x = rb(x.float())
+        f = lambda p: p.detach().to(ACC_DTYPE)
+        x = rb(x.to(ACC_DTYPE))
         t = rb(F.conv2d(x, f(self.patch_embed.proj.weight), f(self.patch_embed.proj.bias),
                         stride=self.cfg.patch_size).flatten(2).transpose(1, 2))
         t = torch.cat((f(self.cls_token).expand(B, -1, -1), t), dim=1)
@@ -243,7 +264,7 @@ class _ContractableLayerNorm(nn.LayerNorm):
 
     def forward(self, x):
         if self.contract:
-            return contract_layernorm(x, self.weight.detach().float(), self.bias.detach().float(), self.eps)
+            return contract_layernorm(x, self.weight.detach().to(ACC_DTYPE), self.bias.detach().to(ACC_DTYPE), self.eps)
         return super().forward(x)
 
 

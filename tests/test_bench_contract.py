@@ -39,3 +39,36 @@ def test_b200_arm_json_line():
     rf = d["roofline"]
     assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0 < rf["frac"] < 1.5 and rf["peak"] > 0
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_b200_arm_parity_block_and_cpu_baseline():
+    """The same-run parity gates of SURVEY.md section 8d (small sample so the test stays short)."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "3", "--hyp", "16",
+                        "--chunk", "17", "--layer", "2", "--ref-hyp", "4"], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    p = d["parity"]
+    assert p["rgb_equal"] and p["depth_equal"] and p["argmax_equal"] and p["top3_equal"]
+    assert p["token_rel_l2"] < 4e-3 and p["scores_max_bf16_ulp"] <= 1.0 and p["tco_max_abs_diff"] < 1e-9
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert "forward_mesh" in d["e2e"]["api"]
+
+
+@pytest.mark.gpu
+def test_b200_arm_strong_scaling_two_gpus():
+    """--scaling strong under torchrun: hypotheses of one proposal sharded over 2 ranks, fp_allgather_scores (NCCL from
+    the C ABI), top-k after the gather, identical on both ranks and equal to the single-GPU result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "bench.py"), "--gpus", "2",
+                        "--scaling", "strong", "--steps", "2", "--warmup", "3", "--hyp", "33", "--chunk", "34",
+                        "--layer", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert d["strong_scaling"]["identical_on_all_ranks"] and d["strong_scaling"]["equal_to_single_gpu"]
+    assert d["strong_scaling"]["hypotheses_per_rank"] == 17

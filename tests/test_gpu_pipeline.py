@@ -1,10 +1,11 @@
 """GPU (-m gpu): the ViT engine and the reference-shaped estimators against the CPU oracle pipeline.
 
 End-to-end tolerance.  bf16 rounding makes deep stacks chaotic: two CPU realisations of the SAME rounding contract
-that differ only in fp32 accumulation order (fp32 vs fp64 accumulate) drift apart by 6.8e-4 rel-L2 after one block
-and 8.5e-3 after 22 (measured, DESIGN.md "Parity").  So: every kernel is held to 1e-3 on identical inputs
-(test_gpu_kernels.py), a single full block to 2e-3, and the full depth to the drift the arithmetic itself allows
-(REL_E2E), plus "no further from fp32 ground truth than PyTorch-eager bf16 is".
+that differ only in accumulation precision (fp32 vs fp64) drift apart by 9.1e-4 rel-L2 after one block and 7.9e-3
+after 22 -- that is a TEST (tests/test_oracle_vit.py::test_contract_drift_fp32_vs_fp64_accumulation).  So: every kernel
+is held to 1e-3 on identical inputs (test_gpu_kernels.py), a single full block to 2e-3, and the full depth to 1.5 x the
+drift the arithmetic itself shows (REL_E2E; the engine's measured value is recorded by tests/test_gpu_full_config.py),
+plus "no further from fp32 ground truth than PyTorch-eager bf16 is".
 """
 import numpy as np
 import pytest
@@ -14,7 +15,7 @@ pytestmark = pytest.mark.gpu
 bf = torch.bfloat16
 dev = "cuda"
 REL_BLOCK = 2e-3
-REL_E2E = 2e-2
+REL_E2E = 1.5 * 7.9e-3   # 1.5 x CONTRACT_DRIFT_FP32_VS_FP64[22] (tests/test_oracle_vit.py)
 
 
 def rel_l2(a, b):
@@ -336,3 +337,38 @@ def test_cli_dino_inference_and_video_synthetic(lib, tmp_path):
     assert 0.5 < float(dv["t"][0].split()[2]) < 10.0  # metres in the video CSV
     nr = cli.run_dino_inference_video(["--synthetic", "1", "--no_rescore", "--out", str(tmp_path / "nr.csv")] + common)
     assert len(pd.read_csv(nr)) == len(df)
+
+
+def test_hypothesis_sharded_forward_equals_unsharded(small_setup):
+    """the hypotheses of ONE proposal split contiguously over W ranks, scores written
+    into the gather buffer, top-k AFTER the gather.  Emulated on one GPU: the W 'ranks' run one after the other on the
+    same buffer (the collective is then the identity), for W that do and do not divide the 24 hypotheses."""
+    from freepose_b200.distributed import shard_bounds
+    mesh, est, _, query, _ = small_setup
+    K = np.array([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
+    bbox = np.array([200.0, 150.0, 330.0, 290.0])
+    want = est.forward_mesh(query, mesh, K, bbox, 0.3, layer=2, k=3)
+
+    class InProcessGather:
+        def __init__(self, n, world):
+            self.n, self.world, self.per = n, world, -(-n // world)
+            self.buf = torch.full((world * self.per,), float("-inf"), dtype=torch.float32, device=dev)
+
+        def local_view(self, rank):
+            return self.buf[rank * self.per:(rank + 1) * self.per]
+
+        def gather(self, rank):
+            return self.buf[:self.n]
+
+    for world in (2, 5, 8):
+        sg = InProcessGather(24, world)
+        outs = [est.forward_mesh(query, mesh, K, bbox, 0.3, layer=2, k=3, shard=(r, world, sg)) for r in range(world)]
+        got = outs[-1]                                   # the last 'rank' sees the complete buffer
+        assert torch.equal(got["all_scores"], want["all_scores"]), world
+        assert got["top_indices"].tolist() == want["top_indices"].tolist()
+        assert np.array_equal(got["scores"], want["scores"])
+        for a, b in zip(got["TCO"], want["TCO"]):
+            assert np.array_equal(a, b)
+        assert torch.isinf(sg.buf[24:]).all()            # padding slots stay at -inf
+        lo, hi = shard_bounds(24, world - 1, world)
+        assert hi == 24

@@ -127,3 +127,51 @@ def test_src_overlay_exposes_the_reference_names():
                       ("src.utils.bbox_utils", "CropResizePad")):
         obj = getattr(importlib.import_module(mod), name)
         assert obj.__module__.startswith("freepose_b200."), (mod, name, obj.__module__)
+
+
+def test_feature_cache_lru_evict_and_reload(tmp_path):
+    """Row K (reference pose_estimator.py:38-77): RAM LRU of `cache_size` meshes kept on the HOST, oldest entry evicted
+    to `<cache_dir>/<name>.pth`, reloaded from disk on the next request, `save_all` writes through, the cache
+    directory is removed with the estimator.  Runs on the CPU with a counting stand-in for the ViT."""
+    from freepose_b200.pipeline.estimators.pose_estimator import DinoPoseEstimator
+
+    class FakeEngine:
+        device = torch.device("cpu")
+
+    class FakeExtractor(torch.nn.Module):
+        engine = FakeEngine()
+
+    calls = []
+
+    class Est(DinoPoseEstimator):
+        def _extract_features(self, proposals, layer=22, batch_size=128):
+            calls.append(float(proposals.flatten()[0]))
+            return (proposals.flatten()[0] * torch.ones(len(proposals), 4, 1024)).to(torch.bfloat16)
+
+    cdir = tmp_path / "cache"
+    est = Est(n_poses=4, cache_size=2, cache_dir=str(cdir), feature_extractor=FakeExtractor(), resolution=224,
+              device_cache_bytes=3 * 4 * 1024 * 2)                      # room for ONE entry on the "device"
+    td = lambda name, v: {"model_name": name, "templates": torch.full((3, 3, 28, 28), float(v))}
+    fa = est._get_template_features(td("a", 1))
+    fb = est._get_template_features(td("b", 2))
+    assert calls == [1.0, 2.0] and list(est.feature_cache) == ["a", "b"] and not list(cdir.glob("*.pth"))
+    assert list(est._device_cache) == ["b"]                             # byte cap: only the most recent stays resident
+    assert all(not t.is_cuda for t in est.feature_cache.values())       # the LRU itself is host memory
+    # hit: no recompute, moves to the MRU end, value identical
+    assert torch.equal(est._get_template_features(td("a", 1)), fa) and calls == [1.0, 2.0]
+    assert list(est.feature_cache) == ["b", "a"]
+    # third mesh: "b" (least recently used) is evicted to disk
+    est._get_template_features(td("c", 3))
+    assert list(est.feature_cache) == ["a", "c"] and [p.name for p in cdir.glob("*.pth")] == ["b.pth"]
+    assert "b" not in est._device_cache
+    # reload "b" from disk: no recompute, bit-identical, and now "a" is the one evicted
+    fb2 = est._get_template_features(td("b", 2))
+    assert calls == [1.0, 2.0, 3.0] and torch.equal(fb2.cpu(), fb.cpu()) and fb2.dtype == torch.bfloat16
+    assert list(est.feature_cache) == ["c", "b"] and (cdir / "a.pth").exists()
+    # save_all writes through immediately
+    est.save_all = True
+    est._get_template_features(td("d", 4))
+    assert (cdir / "d.pth").exists() and torch.equal(torch.load(cdir / "d.pth"), est.feature_cache["d"])
+    # reference __del__ (pose_estimator.py:76-77): the cache directory goes with the estimator
+    est.__del__()
+    assert not cdir.exists()
