@@ -657,6 +657,13 @@ int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale,
   FP_REQUIRE(B > 0 && H > 0 && T > 0, "attention: empty problem");
   const int tpad = (T + 15) / 16 * 16;
   if (tpad > MAX_TPAD) return attention_long_bf16(qkv, out, B, T, H, scale, stream);  // crops above 224^2
+  {
+    // 224^2 crops: the two-stream kernel.  FP_ATTN_SPLIT=0 selects the single-stream kernel below (A/B measurements);
+    // FP_ATTN_POLY=0x1111 / 0x5555 moves 25 / 50 % of the exponentials to the FMA pipe.
+    static const int use_split = [] { const char* e = getenv("FP_ATTN_SPLIT"); return e ? atoi(e) : 1; }();
+    static const unsigned poly = [] { const char* e = getenv("FP_ATTN_POLY"); return e ? unsigned(strtoul(e, nullptr, 0)) : 0u; }();
+    if (T == 261 && use_split) return attention_split_bf16(qkv, out, B, T, H, scale, poly, stream);
+  }
   const int rem = T % QT;
   const int n_tail = (rem > 0 && rem <= TAIL_MAX) ? rem : 0;
   const int n_normal = T / QT + ((rem > TAIL_MAX) ? 1 : 0);

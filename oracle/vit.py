@@ -155,14 +155,51 @@ SINGLE_PASS_KEYS = 272   # padded keys the single-pass kernel holds in TMEM (fre
 KEY_BLOCK = 256          # key block of the tiled-key kernel (freepose_b200/csrc/attention_long.cu)
 
 
+SPLIT_TOKENS = 261       # 224^2 crops: the two-stream kernel (freepose_b200/csrc/attention_split.cu)
+SPLIT_KEYS = 144         # stream 0 = keys [0, 144), stream 1 = keys [144, N)
+
+
+def contract_attention_split(q, k, v, scale, split=SPLIT_KEYS, tile=128):
+    """Split-key flash attention, the arithmetic of attention_split.cu: the keys of every full 128-row query tile are
+    dealt to two independent streams, each with its own row max m_h, un-normalised bf16 P_h = bf16(exp(s - m_h)), fp32
+    row sum l_h of the unrounded p and accumulator O_h = P_h V_h; the tile ends with
+    O = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1), a_h = exp(m_h - max(m_0, m_1)), rounded once.  (The same as two key
+    blocks of an online softmax.)  The N % 128 leftover query rows (cls + registers come first, so these are the last
+    patch rows) are computed by CUDA-core warps in ONE pass over all keys."""
+    N = k.shape[-2]
+    full = N // tile * tile
+    s = (q @ k.transpose(-2, -1)) * scale
+    out = torch.empty_like(q)
+    # full tiles: two streams
+    parts = []
+    for lo, hi in ((0, split), (split, N)):
+        sh = s[..., :full, lo:hi]
+        m = sh.amax(dim=-1, keepdim=True)
+        p = torch.exp(sh - m)
+        parts.append((m, p.sum(dim=-1, keepdim=True), rb(p) @ v[..., lo:hi, :]))
+    (m0, l0, o0), (m1, l1, o1) = parts
+    mm = torch.maximum(m0, m1)
+    a0, a1 = torch.exp(m0 - mm), torch.exp(m1 - mm)
+    out[..., :full, :] = (o0 * a0 + o1 * a1) / (l0 * a0 + l1 * a1)
+    # leftover rows: single pass
+    st = s[..., full:, :]
+    mt = st.amax(dim=-1, keepdim=True)
+    pt = torch.exp(st - mt)
+    out[..., full:, :] = (rb(pt) @ v) / pt.sum(dim=-1, keepdim=True)
+    return rb(out)
+
+
 def contract_attention(q, k, v, scale, key_block=None):
     """Flash/xformers-style attention on bf16-valued fp32 tensors (B, H, N, hd).
 
-    Up to SINGLE_PASS_KEYS keys the softmax is a single pass; above that (crops larger than 224^2) it is the
+    261 tokens (224^2 crops, the headline shape) run the two-stream form (contract_attention_split).  Otherwise, up to
+    SINGLE_PASS_KEYS keys the softmax is a single pass; above that (crops larger than 224^2) it is the
     block-wise online softmax of flash attention with KEY_BLOCK keys per block: the bf16 P of block b is taken
     against the running max after block b, and O / l are rescaled by exp(m_old - m_new) between blocks.
     """
     N = k.shape[-2]
+    if key_block is None and N == SPLIT_TOKENS:
+        return contract_attention_split(q, k, v, scale)
     if key_block is None:
         key_block = KEY_BLOCK if (N + 15) // 16 * 16 > SINGLE_PASS_KEYS else 0
     if not key_block or N <= key_block:

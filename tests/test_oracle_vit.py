@@ -95,3 +95,23 @@ def test_contract_drift_fp32_vs_fp64_accumulation():
     vals = [((a[d] - b[d]).norm() / b[d].norm()).item() for d in sorted(a)]
     assert vals == sorted(vals)
     assert V.ACC_DTYPE == torch.float32
+
+
+def test_split_key_contract_is_as_accurate_as_single_pass():
+    """attention_split.cu deals the keys of a query tile to two streams with private row maxima.  That changes WHERE the
+    un-normalised P is rounded to bf16 (relative to which maximum), not how accurately: against exact (fp64) softmax
+    attention the two-stream contract and the single-pass contract are equally far, on flat and on peaked softmaxes --
+    and both are flash-attention forms (xformers', which the reference installs, is block-wise too)."""
+    from oracle.vit import contract_attention, contract_attention_split
+    torch.manual_seed(0)
+    for gain in (1.0, 4.0):
+        q, k, v = [(torch.randn(2, 4, 261, 64) * (gain if i < 2 else 1)).to(torch.bfloat16).float() for i in range(3)]
+        exact = (torch.softmax((q.double() @ k.double().transpose(-2, -1)) * 0.125, -1) @ v.double())
+        split = contract_attention_split(q, k, v, 0.125).double()
+        single = contract_attention(q, k, v, 0.125, key_block=0).double()
+        e_split = ((split - exact).norm() / exact.norm()).item()
+        e_single = ((single - exact).norm() / exact.norm()).item()
+        assert abs(e_split - e_single) < 0.1 * e_single, (gain, e_split, e_single)
+        assert torch.equal(split[..., 256:, :], single[..., 256:, :])        # leftover rows: the same single pass
+    # dispatch: 261 tokens -> split, everything else unchanged
+    assert torch.equal(contract_attention(q, k, v, 0.125), contract_attention_split(q, k, v, 0.125))
