@@ -293,6 +293,8 @@ def run_b200(args):
     # ---- warm-up, then the device-resident timed region (value) with live per-kernel events
     for _ in range(max(args.warmup, 3)):
         last = step_device()
+    if world > 1:
+        sg.gather(rank)                                    # NCCL sets its transports up lazily at the first collective
     barrier()
     lib.fp_profile_reset()
     lib.fp_profile_enable(1)
