@@ -21,6 +21,12 @@
 // trimesh.PointCloud inputs (renderer.py:46-51) are GL points of size 1: a one-pixel square sprite centred on the
 // projected vertex, flat vertex colour, the vertex's own depth.
 //
+// Near / far planes and the guard band: a triangle with a vertex that does not project (Z <= znear, Z >= zfar, or more
+// than 16384 px off screen) is NOT dropped.  It is rasterised in homogeneous form (Olano & Greer): with camera-space
+// vertices P0..P2 and the sample ray d = ((sx - cx)/fx, (sy - cy)/fy, 1), b_i = sign(det) d.(P_{i+1} x P_{i+2}); covered
+// iff all b_i >= 0 and sum > 0; depth |det| / sum; the per-sample test znear < z < zfar then removes exactly what GL's
+// clipping against the near / far planes removes.  Only views that contain such a vertex run that kernel at all.
+//
 // Kernels: clear keys -> vertex transform -> triangle (32-bit edge functions for small triangles, warp-cooperative walk
 // for large ones) or point scatter -> resolve (one thread per pixel; coalesced depth, shuffle-assembled RGB words).
 #include "common.cuh"
@@ -53,10 +59,35 @@ clear_keys_kernel(unsigned long long* __restrict__ keys, size_t n) {
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = ~0ull;
 }
 
+// camera description shared by the kernels that need camera-space positions again (hard triangles)
+struct Camera {
+  const float* verts;     // [V,3]
+  const float* poses;     // [B,12]
+  const float* view_k;    // [B,4] or nullptr
+  float fx, fy, cx, cy;
+  float znear, zfar;
+};
+
+__device__ __forceinline__ void view_intrinsics(const Camera& cam, int b, float& fx, float& fy, float& cx, float& cy) {
+  fx = cam.fx; fy = cam.fy; cx = cam.cx; cy = cam.cy;
+  if (cam.view_k != nullptr) {
+    fx = cam.view_k[4 * b]; fy = cam.view_k[4 * b + 1]; cx = cam.view_k[4 * b + 2]; cy = cam.view_k[4 * b + 3];
+  }
+}
+
+// cam = R * v + t, evaluated as ((r0*x + r1*y) + r2*z) + t
+__device__ __forceinline__ void camera_point(const float* __restrict__ verts, const float* __restrict__ P, int i,
+                                             float out[3]) {
+  const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+  out[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], x), __fmul_rn(P[1], y)), __fmul_rn(P[2], z)), P[3]);
+  out[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4], x), __fmul_rn(P[5], y)), __fmul_rn(P[6], z)), P[7]);
+  out[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[8], x), __fmul_rn(P[9], y)), __fmul_rn(P[10], z)), P[11]);
+}
+
 __global__ void __launch_bounds__(256)
 vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, ScreenVertex* __restrict__ sv,
               int V, int B, float fx, float fy, float cx, float cy, const float* __restrict__ view_k, float ZNEAR,
-              float ZFAR) {
+              float ZFAR, int* __restrict__ view_hard) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= V) return;
@@ -83,6 +114,7 @@ vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, 
       o.x = int(uf); o.y = int(vf); o.z = Z; o.iz = __fdiv_rn(1.0f, Z);
     }
   }
+  if (o.x == INT_MIN) view_hard[b] = 1;   // this view has triangles for the homogeneous path (benign race: all write 1)
   sv[size_t(b) * V + i] = o;
 }
 
@@ -292,6 +324,139 @@ point_kernel(const ScreenVertex* __restrict__ sv, unsigned long long* __restrict
   }
 }
 
+// ---- hard triangles (see the header): homogeneous rasterisation; oracle/raster_ref.c hard_setup / hard_weights ----------
+struct Hard {
+  float n0[3], n1[3], n2[3];
+  float adet, sgn;
+  int xlo, xhi, ylo, yhi;
+  int valid;
+};
+
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
+  o[0] = __fadd_rn(__fmul_rn(a[1], b[2]), -__fmul_rn(a[2], b[1]));
+  o[1] = __fadd_rn(__fmul_rn(a[2], b[0]), -__fmul_rn(a[0], b[2]));
+  o[2] = __fadd_rn(__fmul_rn(a[0], b[1]), -__fmul_rn(a[1], b[0]));
+}
+
+__device__ __noinline__ void hard_setup(const float* p0, const float* p1, const float* p2, float fx, float fy, float cx,
+                                        float cy, float ZNEAR, float ZFAR, int res, int cull, Hard& h) {
+  h.valid = 0;
+  // entirely in front of the near plane or behind the far plane: nothing survives the per-sample depth test
+  if (!(p0[2] > ZNEAR) && !(p1[2] > ZNEAR) && !(p2[2] > ZNEAR)) return;
+  if (!(p0[2] < ZFAR) && !(p1[2] < ZFAR) && !(p2[2] < ZFAR)) return;
+  cross3(p1, p2, h.n0); cross3(p2, p0, h.n1); cross3(p0, p1, h.n2);
+  const float det = __fadd_rn(__fadd_rn(__fmul_rn(p0[0], h.n0[0]), __fmul_rn(p0[1], h.n0[1])), __fmul_rn(p0[2], h.n0[2]));
+  if (!(det != 0.f) || !(det == det)) return;
+  if (cull && det > 0.f) return;   // sign(det) = sign of the projected area: same rule as the fixed-point path
+  h.sgn = det > 0.f ? 1.0f : -1.0f;
+  h.adet = fabsf(det);
+  // conservative pixel bounds: projections of the vertices in front of the near plane and of the edge / near-plane
+  // intersections, +-1 px; anything not finite -> the whole viewport
+  const float* v[3] = {p0, p1, p2};
+  float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float* a = v[i];
+    const float* b = v[(i + 1) % 3];
+    if (a[2] > ZNEAR) {
+      const float u = __fadd_rn(__fdiv_rn(__fmul_rn(fx, a[0]), a[2]), cx), w = __fadd_rn(__fdiv_rn(__fmul_rn(fy, a[1]), a[2]), cy);
+      umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+      if (!(fabsf(u) < 1.0e9f) || !(fabsf(w) < 1.0e9f)) finite = false;
+    }
+    if ((a[2] > ZNEAR) != (b[2] > ZNEAR)) {
+      const float t = __fdiv_rn(__fadd_rn(ZNEAR, -a[2]), __fadd_rn(b[2], -a[2]));
+      const float X = __fadd_rn(a[0], __fmul_rn(t, __fadd_rn(b[0], -a[0]))), Y = __fadd_rn(a[1], __fmul_rn(t, __fadd_rn(b[1], -a[1])));
+      const float u = __fadd_rn(__fdiv_rn(__fmul_rn(fx, X), ZNEAR), cx), w = __fadd_rn(__fdiv_rn(__fmul_rn(fy, Y), ZNEAR), cy);
+      umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+      if (!(fabsf(u) < 1.0e9f) || !(fabsf(w) < 1.0e9f)) finite = false;
+    }
+  }
+  if (finite) {
+    h.xlo = int(fmaxf(__fadd_rn(floorf(umin), -1.0f), 0.f)); h.xhi = int(fminf(__fadd_rn(floorf(umax), 1.0f), float(res - 1)));
+    h.ylo = int(fmaxf(__fadd_rn(floorf(vmin), -1.0f), 0.f)); h.yhi = int(fminf(__fadd_rn(floorf(vmax), 1.0f), float(res - 1)));
+  } else {
+    h.xlo = 0; h.xhi = res - 1; h.ylo = 0; h.yhi = res - 1;
+  }
+  h.valid = h.xlo <= h.xhi && h.ylo <= h.yhi;
+}
+
+// weights of the fixed-point sample position (sx, sy); true if covered (b_i >= 0, sum > 0)
+__device__ __forceinline__ bool hard_weights(const Hard& h, float fx, float fy, float cx, float cy, long long sx,
+                                             long long sy, float b[3], float& sum) {
+  const float dx = __fdiv_rn(__fadd_rn(__fmul_rn(__ll2float_rn(sx), 0.00390625f), -cx), fx);
+  const float dy = __fdiv_rn(__fadd_rn(__fmul_rn(__ll2float_rn(sy), 0.00390625f), -cy), fy);
+  b[0] = __fmul_rn(h.sgn, __fadd_rn(__fadd_rn(__fmul_rn(dx, h.n0[0]), __fmul_rn(dy, h.n0[1])), h.n0[2]));
+  b[1] = __fmul_rn(h.sgn, __fadd_rn(__fadd_rn(__fmul_rn(dx, h.n1[0]), __fmul_rn(dy, h.n1[1])), h.n1[2]));
+  b[2] = __fmul_rn(h.sgn, __fadd_rn(__fadd_rn(__fmul_rn(dx, h.n2[0]), __fmul_rn(dy, h.n2[1])), h.n2[2]));
+  sum = __fadd_rn(__fadd_rn(b[0], b[1]), b[2]);
+  return b[0] >= 0.f && b[1] >= 0.f && b[2] >= 0.f && sum > 0.f;
+}
+
+__device__ __forceinline__ float hard_interp(const float b[3], float sum, float a0, float a1, float a2) {
+  return __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(b[0], a0), __fmul_rn(b[1], a1)), __fmul_rn(b[2], a2)), sum);
+}
+
+// One thread per (view, face) like triangle_kernel, but only views flagged by the vertex kernel do anything, and only
+// faces with a vertex that did not project.  The warp then walks the pixel bounds of one such triangle at a time.
+template <int S>
+__global__ void __launch_bounds__(256)
+hard_triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ faces, const Camera cam,
+                     const int* __restrict__ view_hard, unsigned long long* __restrict__ keys, int V, int F, int res,
+                     int cull) {
+  const int b = blockIdx.y;
+  if (!view_hard[b]) return;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const ScreenVertex* svb = sv + size_t(b) * V;
+  unsigned long long* keys_view = keys + size_t(b) * res * res * S;
+  float fx, fy, cx, cy;
+  view_intrinsics(cam, b, fx, fy, cx, cy);
+  Hard h;
+  h.valid = 0;
+  if (f < F) {
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    if (svb[i0].x == INT_MIN || svb[i1].x == INT_MIN || svb[i2].x == INT_MIN) {
+      const float* P = cam.poses + size_t(b) * 12;
+      float p0[3], p1[3], p2[3];
+      camera_point(cam.verts, P, i0, p0); camera_point(cam.verts, P, i1, p1); camera_point(cam.verts, P, i2, p2);
+      hard_setup(p0, p1, p2, fx, fy, cx, cy, cam.znear, cam.zfar, res, cull, h);
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, h.valid != 0);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    Hard u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      u.n0[i] = __shfl_sync(0xffffffffu, h.n0[i], src);
+      u.n1[i] = __shfl_sync(0xffffffffu, h.n1[i], src);
+      u.n2[i] = __shfl_sync(0xffffffffu, h.n2[i], src);
+    }
+    u.adet = __shfl_sync(0xffffffffu, h.adet, src);
+    u.sgn = __shfl_sync(0xffffffffu, h.sgn, src);
+    u.xlo = __shfl_sync(0xffffffffu, h.xlo, src); u.xhi = __shfl_sync(0xffffffffu, h.xhi, src);
+    u.ylo = __shfl_sync(0xffffffffu, h.ylo, src); u.yhi = __shfl_sync(0xffffffffu, h.yhi, src);
+    const unsigned uf = unsigned(__shfl_sync(0xffffffffu, f, src));
+    const int uw = u.xhi - u.xlo + 1, uh = u.yhi - u.ylo + 1;
+    for (int i = lane; i < uw * uh; i += 32) {
+      const int py = u.ylo + i / uw, px = u.xlo + i % uw;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const long long sx = ((long long)px << SUB) + c_sample_off[S == 4][s][0];
+        const long long sy = ((long long)py << SUB) + c_sample_off[S == 4][s][1];
+        float bw[3], sum;
+        if (hard_weights(u, fx, fy, cx, cy, sx, sy, bw, sum)) {
+          const float z = __fdiv_rn(u.adet, sum);
+          if (z > cam.znear && z < cam.zfar)
+            atomicMin(&keys_view[(size_t(py) * res + px) * S + s], ((unsigned long long)__float_as_uint(z) << 32) | uf);
+        }
+      }
+    }
+  }
+}
+
 struct Surface {
   const uint8_t* colors;    // [V,3] or nullptr
   const float* uv;          // [V,2] or nullptr
@@ -360,12 +525,55 @@ __device__ __forceinline__ float lod_from_rho2(float rho2, int levels) {
 // Shade triangle `face` at the centre of pixel (px, py): perspective-correct interpolation of vertex colours and / or
 // texture coordinates, x2 ambient, gamma LUT -> unorm8.  MODE 0 = vertex colours, 1 = texture (times vertex colours
 // when sf.colors is set).
+// Interpolated attributes of a HARD triangle at a pixel centre: vertex colour vc[3], texture coordinate (u, v) and its
+// finite differences to the neighbouring pixel centres (in texels).  Kept out of line: the common path must not pay
+// registers for it.
+__device__ __noinline__ void hard_attributes(const Camera& cam, int b, int res, const Surface& sf, int i0, int i1, int i2,
+                                             int px, int py, bool want_colors, bool want_uv, float vc[3], float uvd[6]) {
+  float fx, fy, cx, cy;
+  view_intrinsics(cam, b, fx, fy, cx, cy);
+  const float* P = cam.poses + size_t(b) * 12;
+  float p0[3], p1[3], p2[3];
+  camera_point(cam.verts, P, i0, p0); camera_point(cam.verts, P, i1, p1); camera_point(cam.verts, P, i2, p2);
+  Hard h;
+  hard_setup(p0, p1, p2, fx, fy, cx, cy, cam.znear, cam.zfar, res, 0, h);
+  const long long sx = ((long long)px << SUB) + 128, sy = ((long long)py << SUB) + 128;
+  float bw[3], sum;
+  hard_weights(h, fx, fy, cx, cy, sx, sy, bw, sum);
+  if (want_colors) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      vc[ch] = hard_interp(bw, sum, float(sf.colors[3 * i0 + ch]), float(sf.colors[3 * i1 + ch]), float(sf.colors[3 * i2 + ch]));
+  }
+  if (want_uv) {
+    const float ua = sf.uv[2 * i0], ub = sf.uv[2 * i1], uc = sf.uv[2 * i2];
+    const float va = sf.uv[2 * i0 + 1], vb = sf.uv[2 * i1 + 1], vcc = sf.uv[2 * i2 + 1];
+    const float u = hard_interp(bw, sum, ua, ub, uc), v = hard_interp(bw, sum, va, vb, vcc);
+    float bx[3], sumx, by[3], sumy;
+    hard_weights(h, fx, fy, cx, cy, sx + ONE, sy, bx, sumx);
+    hard_weights(h, fx, fy, cx, cy, sx, sy + ONE, by, sumy);
+    const float fw = float(sf.tex_w), fh = float(sf.tex_h);
+    uvd[0] = u; uvd[1] = v;
+    uvd[2] = __fmul_rn(__fadd_rn(hard_interp(bx, sumx, ua, ub, uc), -u), fw);
+    uvd[3] = __fmul_rn(__fadd_rn(hard_interp(bx, sumx, va, vb, vcc), -v), fh);
+    uvd[4] = __fmul_rn(__fadd_rn(hard_interp(by, sumy, ua, ub, uc), -u), fw);
+    uvd[5] = __fmul_rn(__fadd_rn(hard_interp(by, sumy, va, vb, vcc), -v), fh);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, const int* __restrict__ faces,
-                                      const Surface& sf, unsigned face, int px, int py, int out[3]) {
+                                      const Surface& sf, const Camera& cam, int b, int res, unsigned face, int px, int py,
+                                      int out[3]) {
   const int i0 = faces[3 * face], i1 = faces[3 * face + 1], i2 = faces[3 * face + 2];
   ScreenVertex v0 = svb[i0], v1 = svb[i1], v2 = svb[i2];
   int c0 = i0, c1 = i1, c2 = i2;
+  const bool hard = v0.x == INT_MIN || v1.x == INT_MIN || v2.x == INT_MIN;
+  float h_vc[3], h_uvd[6];   // (only written and read on the hard path)
+  if (hard) {
+    h_vc[0] = h_vc[1] = h_vc[2] = 255.f;
+    hard_attributes(cam, b, res, sf, i0, i1, i2, px, py, MODE == 0 || sf.colors != nullptr, MODE == 1, h_vc, h_uvd);
+  }
   long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
   if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
   const float fa = __ll2float_rn(area);
@@ -386,7 +594,9 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   float w0, w1, w2, wsum;
   weights(sx, sy, w0, w1, w2, wsum);
   float vc[3] = {255.f, 255.f, 255.f};
-  if (MODE == 0 || sf.colors != nullptr) {
+  if (hard) {
+    vc[0] = h_vc[0]; vc[1] = h_vc[1]; vc[2] = h_vc[2];
+  } else if (MODE == 0 || sf.colors != nullptr) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
       vc[ch] = interp(w0, w1, w2, wsum, float(sf.colors[3 * c0 + ch]), float(sf.colors[3 * c1 + ch]),
@@ -400,16 +610,17 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   }
   const float ua = sf.uv[2 * c0], ub = sf.uv[2 * c1], uc = sf.uv[2 * c2];
   const float va = sf.uv[2 * c0 + 1], vb = sf.uv[2 * c1 + 1], vcc = sf.uv[2 * c2 + 1];
-  const float u = interp(w0, w1, w2, wsum, ua, ub, uc), v = interp(w0, w1, w2, wsum, va, vb, vcc);
+  float u = interp(w0, w1, w2, wsum, ua, ub, uc), v = interp(w0, w1, w2, wsum, va, vb, vcc);
   // footprint from the neighbouring pixel centres (the finite differences GL takes inside a 2x2 quad)
   float x0w, x1w, x2w, xs, y0w, y1w, y2w, ys;
   weights(sx + ONE, sy, x0w, x1w, x2w, xs);
   weights(sx, sy + ONE, y0w, y1w, y2w, ys);
   const float fw = float(sf.tex_w), fh = float(sf.tex_h);
-  const float dux = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, ua, ub, uc), -u), fw);
-  const float dvx = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, va, vb, vcc), -v), fh);
-  const float duy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, ua, ub, uc), -u), fw);
-  const float dvy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, va, vb, vcc), -v), fh);
+  float dux = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, ua, ub, uc), -u), fw);
+  float dvx = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, va, vb, vcc), -v), fh);
+  float duy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, ua, ub, uc), -u), fw);
+  float dvy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, va, vb, vcc), -v), fh);
+  if (hard) { u = h_uvd[0]; v = h_uvd[1]; dux = h_uvd[2]; dvx = h_uvd[3]; duy = h_uvd[4]; dvy = h_uvd[5]; }
   const float rx = __fadd_rn(__fmul_rn(dux, dux), __fmul_rn(dvx, dvx));
   const float ry = __fadd_rn(__fmul_rn(duy, duy), __fmul_rn(dvy, dvy));
   const float lod = lod_from_rho2(fmaxf(rx, ry), sf.tex_levels);
@@ -442,8 +653,8 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
 template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
-               const int* __restrict__ faces, const Surface sf, uint8_t* __restrict__ rgb, float* __restrict__ depth,
-               int V, int res) {
+               const int* __restrict__ faces, const Surface sf, const Camera cam, uint8_t* __restrict__ rgb,
+               float* __restrict__ depth, int V, int res) {
   const int b = blockIdx.y;
   const int npix = res * res;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,7 +688,7 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
             for (int ch = 0; ch < 3; ++ch)
               col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), sf.ambient_255), sf.gamma_lut);
           } else {
-            shade<MODE>(svb, faces, sf, face, px, py, col);
+            shade<MODE>(svb, faces, sf, cam, b, res, face, px, py, col);
           }
           last_face = face;
         }
@@ -504,8 +715,11 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int S>
-int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* keys, float znear, float zfar,
-                  cudaStream_t stream) {
+int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* keys, const int* view_hard, float znear,
+                  float zfar, cudaStream_t stream) {
+  Camera cam;
+  cam.verts = a.verts; cam.poses = a.poses; cam.view_k = a.view_k;
+  cam.fx = a.fx; cam.fy = a.fy; cam.cx = a.cx; cam.cy = a.cy; cam.znear = znear; cam.zfar = zfar;
   Surface sf;
   sf.ambient = a.ambient > 0.f ? a.ambient : 2.0f;
   sf.ambient_255 = sf.ambient / 255.0f;
@@ -515,15 +729,18 @@ int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* key
   if (a.primitive == 1) {
     point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res, znear, zfar);
     FP_CUDA(cudaGetLastError());
-    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
   } else {
     triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res,
                                                                          a.cull_backfaces, znear, zfar);
     FP_CUDA(cudaGetLastError());
+    hard_triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F,
+                                                                              a.res, a.cull_backfaces);
+    FP_CUDA(cudaGetLastError());
     if (a.texture != nullptr)
-      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
     else
-      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
   }
   FP_CUDA(cudaGetLastError());
   return 0;
@@ -534,7 +751,8 @@ int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* key
 int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
   FP_REQUIRE(msaa == 1 || msaa == 4, "raster: msaa must be 1 or 4");
   FP_REQUIRE(B >= 0 && V >= 0 && res > 0, "raster: bad sizes");
-  *bytes = align_up(size_t(B) * V * sizeof(ScreenVertex), 256) + size_t(B) * res * res * msaa * 8 + 256;
+  *bytes = align_up(size_t(B) * V * sizeof(ScreenVertex), 256) + align_up(size_t(B) * res * res * msaa * 8, 256) +
+           align_up(size_t(B) * sizeof(int), 256) + 256;   // screen vertices | sample keys | per-view "has hard triangles" flags
   return 0;
 }
 
@@ -560,14 +778,17 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(
       reinterpret_cast<uint8_t*>(workspace) + align_up(size_t(a.B) * a.V * sizeof(ScreenVertex), 256));
   const size_t nkeys = size_t(a.B) * a.res * a.res * a.msaa;
-  ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, 4, stream);  // algorithmic bytes: RGB u8 + depth f32 out
+  int* view_hard = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(keys) + align_up(nkeys * 8, 256));
+  ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, a.primitive == 1 ? 4 : 5, stream);  // algorithmic bytes: RGB u8 + depth f32 out
   clear_keys_kernel<<<sm_count() * 8, 256, 0, stream>>>(keys, nkeys);
   FP_CUDA(cudaGetLastError());
+  FP_CUDA(cudaMemsetAsync(view_hard, 0, size_t(a.B) * sizeof(int), stream));
   const float znear = a.znear > 0.f ? a.znear : ZNEAR_DEFAULT, zfar = a.zfar > 0.f ? a.zfar : ZFAR_DEFAULT;
   vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy,
-                                                                  a.view_k, znear, zfar);
+                                                                  a.view_k, znear, zfar, view_hard);
   FP_CUDA(cudaGetLastError());
-  return a.msaa == 4 ? launch_raster<4>(a, sv, keys, znear, zfar, stream) : launch_raster<1>(a, sv, keys, znear, zfar, stream);
+  return a.msaa == 4 ? launch_raster<4>(a, sv, keys, view_hard, znear, zfar, stream)
+                     : launch_raster<1>(a, sv, keys, view_hard, znear, zfar, stream);
 }
 
 }  // namespace fp

@@ -10,6 +10,15 @@
  * CUDA rasteriser implements exactly this written-down specification: sequential loops, a classic z-buffer
  * (no atomics, no binning), compiled with -ffp-contract=off so every fp32 operation rounds once.
  *
+ * Near / far planes and the coordinate guard band.  A triangle whose three vertices all project inside the guard band
+ * with znear < Z < zfar takes the fixed-point path above.  Any other triangle ("hard": it straddles the near plane, has
+ * a vertex behind the camera, beyond zfar, or further than 16384 px off screen) is NOT dropped: GL clips it, and so
+ * does this specification, per sample, by rasterising it in homogeneous form (Olano & Greer 1997): with camera-space
+ * vertices P0,P1,P2 and the sample ray d = ((sx - cx)/fx, (sy - cy)/fy, 1), b_i = sign(det) * d . (P_{i+1} x P_{i+2}),
+ * the sample is covered iff all b_i >= 0 and their sum > 0, its depth is |det| / sum(b_i), and the existing per-sample
+ * test znear < z < zfar cuts the part in front of the near plane (and behind the far plane) away -- exactly what
+ * clipping the triangle against those planes would leave.  Attributes interpolate with the weights b_i / sum.
+ *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC oracle/raster_ref.c -o oracle/_build/libraster_ref.so -lm
  */
 #include <math.h>
@@ -22,7 +31,7 @@
 static float ZNEAR = 0.05f, ZFAR = 100.0f;   /* pyrender IntrinsicsCamera defaults; raster_ref3 may override per call */
 #define COORD_LIMIT (1 << 22)
 
-typedef struct { int x, y, ok; float z, iz; } SV;
+typedef struct { int x, y, ok; float z, iz; float X, Y, Z; } SV;
 
 static const int OFF1[1][2] = {{128, 128}};
 static const int OFF4[4][2] = {{96, 32}, {224, 96}, {32, 160}, {160, 224}};
@@ -34,6 +43,7 @@ static void project(const float* verts, const float* P, int V, float fx, float f
     float Y = ((P[4] * x + P[5] * y) + P[6] * z) + P[7];
     float Z = ((P[8] * x + P[9] * y) + P[10] * z) + P[11];
     sv[i].ok = 0;
+    sv[i].X = X; sv[i].Y = Y; sv[i].Z = Z;
     if (!(Z > ZNEAR) || !(Z < ZFAR)) continue;
     float u = (fx * X) / Z + cx;
     float v = (fy * Y) / Z + cy;
@@ -109,30 +119,125 @@ static Weights persp_weights(SV v0, SV v1, SV v2, float fa, int64_t sx, int64_t 
 }
 static float interp(Weights w, float a0, float a1, float a2) { return ((w.w0 * a0 + w.w1 * a1) + w.w2 * a2) / w.wsum; }
 
+/* ---- hard triangles: homogeneous rasterisation ------------------------------------------------------------------ */
+typedef struct { float n0[3], n1[3], n2[3]; float adet, sgn; int xlo, xhi, ylo, yhi; int valid; } Hard;
+
+static void cross3(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static Hard hard_setup(SV v0, SV v1, SV v2, float fx, float fy, float cx, float cy, int res, int cull) {
+  Hard h;
+  h.valid = 0;
+  /* entirely in front of the near plane or behind the far plane: nothing survives the per-sample depth test */
+  if (!(v0.Z > ZNEAR) && !(v1.Z > ZNEAR) && !(v2.Z > ZNEAR)) return h;
+  if (!(v0.Z < ZFAR) && !(v1.Z < ZFAR) && !(v2.Z < ZFAR)) return h;
+  float p0[3] = {v0.X, v0.Y, v0.Z}, p1[3] = {v1.X, v1.Y, v1.Z}, p2[3] = {v2.X, v2.Y, v2.Z};
+  cross3(p1, p2, h.n0); cross3(p2, p0, h.n1); cross3(p0, p1, h.n2);
+  float det = (p0[0] * h.n0[0] + p0[1] * h.n0[1]) + p0[2] * h.n0[2];
+  if (!(det != 0.f) || !(det == det)) return h;
+  if (cull && det > 0.f) return h;           /* sign(det) = sign of the projected area: same rule as the fixed-point path */
+  h.sgn = det > 0.f ? 1.0f : -1.0f;
+  h.adet = fabsf(det);
+  /* conservative pixel bounds: projections of the vertices in front of the near plane and of the edge / near-plane
+   * intersections, +-1 px; anything not finite -> the whole viewport */
+  const SV* v[3] = {&v0, &v1, &v2};
+  float umin = INFINITY, umax = -INFINITY, vmin = INFINITY, vmax = -INFINITY;
+  int finite = 1;
+  for (int i = 0; i < 3; ++i) {
+    const SV* a = v[i];
+    const SV* b = v[(i + 1) % 3];
+    if (a->Z > ZNEAR) {
+      float u = (fx * a->X) / a->Z + cx, w = (fy * a->Y) / a->Z + cy;
+      umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+      if (!(fabsf(u) < 1.0e9f) || !(fabsf(w) < 1.0e9f)) finite = 0;
+    }
+    if ((a->Z > ZNEAR) != (b->Z > ZNEAR)) {
+      float t = (ZNEAR - a->Z) / (b->Z - a->Z);
+      float X = a->X + t * (b->X - a->X), Y = a->Y + t * (b->Y - a->Y);
+      float u = (fx * X) / ZNEAR + cx, w = (fy * Y) / ZNEAR + cy;
+      umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+      if (!(fabsf(u) < 1.0e9f) || !(fabsf(w) < 1.0e9f)) finite = 0;
+    }
+  }
+  if (finite) {
+    h.xlo = (int)fmaxf(floorf(umin) - 1.0f, 0.f); h.xhi = (int)fminf(floorf(umax) + 1.0f, (float)(res - 1));
+    h.ylo = (int)fmaxf(floorf(vmin) - 1.0f, 0.f); h.yhi = (int)fminf(floorf(vmax) + 1.0f, (float)(res - 1));
+  } else {
+    h.xlo = 0; h.xhi = res - 1; h.ylo = 0; h.yhi = res - 1;
+  }
+  h.valid = h.xlo <= h.xhi && h.ylo <= h.yhi;
+  return h;
+}
+
+/* weights of the fixed-point sample position (sx, sy): returns 1 if covered (b_i >= 0, sum > 0) */
+static int hard_weights(const Hard* h, float fx, float fy, float cx, float cy, int64_t sx, int64_t sy, float b[3],
+                        float* sum) {
+  float dx = ((float)sx * 0.00390625f - cx) / fx, dy = ((float)sy * 0.00390625f - cy) / fy;
+  b[0] = h->sgn * ((dx * h->n0[0] + dy * h->n0[1]) + h->n0[2]);
+  b[1] = h->sgn * ((dx * h->n1[0] + dy * h->n1[1]) + h->n1[2]);
+  b[2] = h->sgn * ((dx * h->n2[0] + dy * h->n2[1]) + h->n2[2]);
+  *sum = (b[0] + b[1]) + b[2];
+  return b[0] >= 0.f && b[1] >= 0.f && b[2] >= 0.f && *sum > 0.f;
+}
+
+static float hard_interp(const float b[3], float sum, float a0, float a1, float a2) {
+  return ((b[0] * a0 + b[1] * a1) + b[2] * a2) / sum;
+}
+
+typedef struct { float fx, fy, cx, cy; int cull, res; } Cam;
+static Cam CAM;
+
 /* colour of triangle f at the centre of pixel (px, py) -> out[3] unorm8 */
 static void shade(const Surface* sf, const int32_t* faces, const SV* sv, int f, int px, int py, int out[3]) {
   int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
   SV v0 = sv[i0], v1 = sv[i1], v2 = sv[i2];
-  int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
-  if (area < 0) { SV t = v1; v1 = v2; v2 = t; int ti = i1; i1 = i2; i2 = ti; area = -area; }
-  float fa = (float)area;
   int64_t sx = ((int64_t)px << SUB) + 128, sy = ((int64_t)py << SUB) + 128;
-  Weights w = persp_weights(v0, v1, v2, fa, sx, sy);
+  const int hard = !v0.ok || !v1.ok || !v2.ok;
   float vc[3] = {255.f, 255.f, 255.f};
-  if (sf->texture == NULL || sf->colors != NULL)
-    for (int ch = 0; ch < 3; ++ch)
-      vc[ch] = interp(w, (float)sf->colors[3 * i0 + ch], (float)sf->colors[3 * i1 + ch], (float)sf->colors[3 * i2 + ch]);
+  float ua = 0.f, ub = 0.f, uc = 0.f, va = 0.f, vb = 0.f, vcc = 0.f, u = 0.f, v = 0.f;
+  float dux = 0.f, dvx = 0.f, duy = 0.f, dvy = 0.f;
+  float fw = (float)sf->tex_w, fh = (float)sf->tex_h;
+  if (hard) {
+    Hard h = hard_setup(v0, v1, v2, CAM.fx, CAM.fy, CAM.cx, CAM.cy, CAM.res, 0);
+    float b[3], sum;
+    hard_weights(&h, CAM.fx, CAM.fy, CAM.cx, CAM.cy, sx, sy, b, &sum);
+    if (sf->texture == NULL || sf->colors != NULL)
+      for (int ch = 0; ch < 3; ++ch)
+        vc[ch] = hard_interp(b, sum, (float)sf->colors[3 * i0 + ch], (float)sf->colors[3 * i1 + ch], (float)sf->colors[3 * i2 + ch]);
+    if (sf->texture != NULL) {
+      ua = sf->uv[2 * i0]; ub = sf->uv[2 * i1]; uc = sf->uv[2 * i2];
+      va = sf->uv[2 * i0 + 1]; vb = sf->uv[2 * i1 + 1]; vcc = sf->uv[2 * i2 + 1];
+      u = hard_interp(b, sum, ua, ub, uc); v = hard_interp(b, sum, va, vb, vcc);
+      float bx[3], sumx, by[3], sumy;
+      hard_weights(&h, CAM.fx, CAM.fy, CAM.cx, CAM.cy, sx + ONE, sy, bx, &sumx);
+      hard_weights(&h, CAM.fx, CAM.fy, CAM.cx, CAM.cy, sx, sy + ONE, by, &sumy);
+      dux = (hard_interp(bx, sumx, ua, ub, uc) + -u) * fw; dvx = (hard_interp(bx, sumx, va, vb, vcc) + -v) * fh;
+      duy = (hard_interp(by, sumy, ua, ub, uc) + -u) * fw; dvy = (hard_interp(by, sumy, va, vb, vcc) + -v) * fh;
+    }
+  } else {
+    int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
+    if (area < 0) { SV t = v1; v1 = v2; v2 = t; int ti = i1; i1 = i2; i2 = ti; area = -area; }
+    float fa = (float)area;
+    Weights w = persp_weights(v0, v1, v2, fa, sx, sy);
+    if (sf->texture == NULL || sf->colors != NULL)
+      for (int ch = 0; ch < 3; ++ch)
+        vc[ch] = interp(w, (float)sf->colors[3 * i0 + ch], (float)sf->colors[3 * i1 + ch], (float)sf->colors[3 * i2 + ch]);
+    if (sf->texture != NULL) {
+      ua = sf->uv[2 * i0]; ub = sf->uv[2 * i1]; uc = sf->uv[2 * i2];
+      va = sf->uv[2 * i0 + 1]; vb = sf->uv[2 * i1 + 1]; vcc = sf->uv[2 * i2 + 1];
+      u = interp(w, ua, ub, uc); v = interp(w, va, vb, vcc);
+      Weights wx = persp_weights(v0, v1, v2, fa, sx + ONE, sy), wy = persp_weights(v0, v1, v2, fa, sx, sy + ONE);
+      dux = (interp(wx, ua, ub, uc) + -u) * fw; dvx = (interp(wx, va, vb, vcc) + -v) * fh;
+      duy = (interp(wy, ua, ub, uc) + -u) * fw; dvy = (interp(wy, va, vb, vcc) + -v) * fh;
+    }
+  }
   if (sf->texture == NULL) {
     for (int ch = 0; ch < 3; ++ch) out[ch] = to_unorm8(vc[ch] * sf->ambient_255, sf->gamma_lut);
     return;
   }
-  float ua = sf->uv[2 * i0], ub = sf->uv[2 * i1], uc = sf->uv[2 * i2];
-  float va = sf->uv[2 * i0 + 1], vb = sf->uv[2 * i1 + 1], vcc = sf->uv[2 * i2 + 1];
-  float u = interp(w, ua, ub, uc), v = interp(w, va, vb, vcc);
-  Weights wx = persp_weights(v0, v1, v2, fa, sx + ONE, sy), wy = persp_weights(v0, v1, v2, fa, sx, sy + ONE);
-  float fw = (float)sf->tex_w, fh = (float)sf->tex_h;
-  float dux = (interp(wx, ua, ub, uc) + -u) * fw, dvx = (interp(wx, va, vb, vcc) + -v) * fh;
-  float duy = (interp(wy, ua, ub, uc) + -u) * fw, dvy = (interp(wy, va, vb, vcc) + -v) * fh;
   float rx = dux * dux + dvx * dvx, ry = duy * duy + dvy * dvy;
   float lod = lod_from_rho2(fmaxf(rx, ry), sf->tex_levels);
   int l0 = (int)lod;
@@ -161,6 +266,7 @@ static void render_view(const float* verts, const int32_t* faces, const Surface*
   const int S = msaa;
   const int (*off)[2] = (S == 4) ? OFF4 : OFF1;
   project(verts, P, V, fx, fy, cx, cy, sv);
+  CAM.fx = fx; CAM.fy = fy; CAM.cx = cx; CAM.cy = cy; CAM.cull = cull; CAM.res = res;
   const size_t ns = (size_t)res * res * S;
   for (size_t i = 0; i < ns; ++i) { zbuf[i] = INFINITY; fbuf[i] = -1; }
   /* GL_POINTS, size 1: square sprite [x-.5, x+.5) x [y-.5, y+.5), flat depth; lower vertex index wins depth ties */
@@ -180,7 +286,23 @@ static void render_view(const float* verts, const int32_t* faces, const Surface*
   }
   for (int f = 0; !sf->points && f < F; ++f) {
     SV v0 = sv[faces[3 * f]], v1 = sv[faces[3 * f + 1]], v2 = sv[faces[3 * f + 2]];
-    if (!v0.ok || !v1.ok || !v2.ok) continue;
+    if (!v0.ok || !v1.ok || !v2.ok) {
+      /* hard triangle: homogeneous rasterisation, clipped per sample by the depth test */
+      Hard h = hard_setup(v0, v1, v2, fx, fy, cx, cy, res, cull);
+      if (!h.valid) continue;
+      for (int py = h.ylo; py <= h.yhi; ++py)
+        for (int px = h.xlo; px <= h.xhi; ++px)
+          for (int s = 0; s < S; ++s) {
+            int64_t sx = ((int64_t)px << SUB) + off[s][0], sy = ((int64_t)py << SUB) + off[s][1];
+            float b[3], sum;
+            if (!hard_weights(&h, fx, fy, cx, cy, sx, sy, b, &sum)) continue;
+            float z = h.adet / sum;
+            if (!(z > ZNEAR && z < ZFAR)) continue;
+            size_t k = ((size_t)py * res + px) * S + s;
+            if (z < zbuf[k]) { zbuf[k] = z; fbuf[k] = f; }
+          }
+      continue;
+    }
     int64_t area = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
     if (area == 0) continue;
     if (cull && area > 0) continue;          /* y-down image: GL front faces have negative area here */

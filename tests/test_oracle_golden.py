@@ -258,3 +258,46 @@ def test_raster_oracle_bilinear_texture_on_a_facing_quad():
     got = rgb[0, 24:200, 24:200].astype(np.float64)
     assert np.abs(got - want).max() <= 1 and np.mean(got == want) > 0.97
     assert got.std() > 20                                                        # a real image, not a constant
+
+
+def test_raster_oracle_clips_at_the_near_plane_like_an_analytic_ray_caster():
+    """The restated spec must CLIP triangles that straddle the near plane or reach behind the camera (GL does), not drop
+    them.  A ground quad from z = -1 (behind the camera) to z = 6: coverage and depth of every pixel against the closed
+    form ray / plane intersection t = 0.3 / d_y, inside |X| < 2, 0.05 < t < 6 -- and vertex colours against the bilinear
+    closed form on the quad's two triangles."""
+    from oracle import raster as R
+    res, f, c = 128, 150.0, 64.0
+    V = np.array([[-2, 0.3, -1.0], [2, 0.3, -1.0], [2, 0.3, 6.0], [-2, 0.3, 6.0]], np.float32)
+    F = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    col = np.array([[250, 10, 10], [10, 250, 10], [10, 10, 250], [250, 250, 10]], np.uint8)
+    rgb, depth = R.render(V, F, col, np.eye(4)[None], f, f, c, c, res, msaa=1)
+    py, px = np.mgrid[0:res, 0:res]
+    dx, dy = (px + 0.5 - c) / f, (py + 0.5 - c) / f
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(dy > 0, 0.3 / dy, np.inf)
+    X = t * dx
+    want = (np.abs(X) < 2) & (t < 6) & (t > 0.05)
+    got = depth[0] > 0
+    assert np.array_equal(got, want) and want.sum() > 5000
+    assert np.max(np.abs(depth[0][want] - t[want]) / t[want]) < 1e-6
+    # colours: barycentric in the plane (exact for perspective-correct interpolation), x ambient 2, gamma 1/2.2
+    P = np.stack([X[want], t[want]], axis=1)                      # (X, Z) on the plane
+    A, B, C, D = V[0, [0, 2]], V[1, [0, 2]], V[2, [0, 2]], V[3, [0, 2]]
+
+    def bary(p, a, b, cc):
+        T = np.array([[b[0] - a[0], cc[0] - a[0]], [b[1] - a[1], cc[1] - a[1]]], np.float64)
+        uv = np.linalg.solve(T, (p - a).T).T
+        return np.stack([1 - uv.sum(1), uv[:, 0], uv[:, 1]], axis=1)
+    w1 = bary(P.astype(np.float64), A, B, C)
+    w2 = bary(P.astype(np.float64), A, C, D)
+    in1 = (w1 >= -1e-9).all(1)
+    lin = np.where(in1[:, None], w1 @ col[[0, 1, 2]].astype(np.float64), w2 @ col[[0, 2, 3]].astype(np.float64)) / 255 * 2
+    expect = np.floor(255 * np.clip(lin, 0, 1) ** (1 / 2.2) + 0.5)
+    diff = np.abs(rgb[0][want].astype(np.float64) - expect)
+    # away from the shared diagonal the interpolated colour is the closed form to LUT rounding
+    interior = (np.abs(w1).min(1) > 1e-3) & (np.abs(w2).min(1) > 1e-3)
+    assert diff[interior].max() <= 1.0
+    # a wall whose far vertices project 60 000 px off screen (outside the fixed-point guard band) is kept as well
+    W = np.array([[-400, -0.5, 1.0], [0.2, -0.5, 2.0], [0.2, 0.2, 2.0], [-400, 0.2, 1.0]], np.float32)
+    _, dw = R.render(W, F, col, np.eye(4)[None], f, f, c, c, res, msaa=1)
+    assert (dw[0, 40:60, :20] > 0).all() and not (dw[0, :10, :] > 0).any()
