@@ -421,6 +421,265 @@ def run_b200(args):
     print(json.dumps(out), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- secondary configs
+# BASELINE.json configs 3, 4 and 5 through the same harness (the headline line stays configs[1] = --config pose).
+def setup_ffa(args, rank, world, dev):
+    """configs[2]: extract_retrieval_features --feature ffa --layer 22 --batch_size 256 over 50k synthetic template
+    renders (reference scripts/extract_retrieval_features.py:40-70)."""
+    from freepose_b200 import ops
+    from freepose_b200.pipeline.estimators.pose_estimator import DinoPoseEstimator
+    from freepose_b200.synthetic import synthetic_mesh
+    from freepose_b200.vit_weights import synthetic_state_dict
+    B = args.batch
+    est = DinoPoseEstimator(n_poses=B, cache_size=0, cache_dir=f"/tmp/fp_bench_ffa_{rank}",
+                            weights=synthetic_state_dict(seed=0, depth=args.layer), resolution=args.res, chunk=B)
+    meshes = [synthetic_mesh(i + 4 * rank, subdivisions=5) for i in range(4)]
+    state = {"i": 0}
+    fe = est.feature_extractor
+
+    def step_device():
+        mesh = meshes[state["i"] % len(meshes)]
+        state["i"] += 1
+        rgb, depth = est.renderer.render_device(mesh)
+        patches, _, mask, _ = est.renderer.proposals_device(rgb, depth, args.res, to_patches=True)
+        feats = fe.forward_patches(patches, res=args.res, layer=args.layer)
+        return ops.ffa_pool(feats, mask)
+
+    # e2e: what the reference script does per mesh -- host templates + masks in, (views, 1024) fp32 out
+    rgb, depth = est.renderer.render_device(meshes[0])
+    templates = (rgb.float() / 255).permute(0, 3, 1, 2).contiguous().cpu().pin_memory()
+    masks = (depth > 0).cpu().pin_memory()
+
+    def step_e2e():
+        feats = fe(templates, layer=args.layer, feature_type="patch")
+        pooled, valid = ops.ffa_pool(feats, masks.to(dev, non_blocking=True))
+        return pooled.cpu().numpy()[(valid > 0).cpu().numpy()]
+
+    steps_for_50k = -(-50000 // (B * world))
+    return dict(metric=f"template images/sec (raster+ViT-L{args.layer}+FFA pool) @{args.res}^2", unit="img/s",
+                units_per_step=B, step_device=step_device, step_e2e=step_e2e,
+                h2d=templates.numel() * 4 + masks.numel(), d2h=B * 1024 * 4 + B * 4,
+                api="DINOv2FeatureExtractor.forward(templates_host, layer, 'patch') + ops.ffa_pool -> .npy rows",
+                flops_per_unit=vit_gflop(args.res, args.layer) * 1e9,
+                workload={"workload": f"extract_retrieval_features --feature ffa --layer {args.layer} --batch_size {B} "
+                                      f"(BASELINE configs[2]): {steps_for_50k * B * world} synthetic template renders at "
+                                      f"--steps {steps_for_50k}", "batch": B, "crop": args.res, "layer": args.layer,
+                          "mesh_faces": 20480, "l2": "activations of a 256-image batch ~1.4 GB >> 126 MB L2"})
+
+
+def setup_refiner(args, rank, world, dev):
+    """configs[4], the part of smooth_poses_video that is the hot-path pattern: TrackingRefiner.pose_confidence for 64
+    refinement renders per frame (reference tracking_refiner.py:45-100): roi_align 518^2 + render at the cropped K +
+    2 x ViT-B/14-reg (1374 tokens) + masked per-patch cosine."""
+    from freepose_b200.pipeline.estimators.tracking_refiner import TrackingRefiner
+    from freepose_b200.pipeline.utils import generate_poses
+    from freepose_b200.synthetic import synthetic_mesh
+    from freepose_b200.vit_weights import VITB14_REG, synthetic_state_dict
+    n = args.batch
+    ref = TrackingRefiner(weights=synthetic_state_dict(VITB14_REG, seed=0), chunk=n)
+    mesh = synthetic_mesh(4 + rank, subdivisions=5, scale=0.1)
+    rng = np.random.default_rng(rank)
+    K = np.array([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
+    frame_dev = torch.rand(3, 480, 640, device=dev)
+    frame_host = (frame_dev * 255).to(torch.uint8).permute(1, 2, 0).contiguous().cpu().pin_memory()
+    Ts = []
+    for p in generate_poses(n):
+        T = np.array(p)
+        T[:3, 3] = [rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(0.5, 0.7)]
+        Ts.append(T)
+    g = 518 // 14
+    tokens = g * g + 5
+    d, mlp, L = VITB14_REG.embed_dim, VITB14_REG.mlp_dim, VITB14_REG.depth
+    flops = 2 * (2 * 588 * d * g * g + L * ((8 * d * d + 4 * d * mlp) * tokens + 4 * tokens * tokens * d))   # 2 forwards per render
+    return dict(metric="refinement renders/sec (roi_align+raster+2xViT-B/14@518^2+masked cosine)", unit="renders/s",
+                units_per_step=n, step_device=lambda: ref.pose_confidences(mesh, [frame_dev] * n, K, Ts),
+                step_e2e=lambda: ref.pose_confidences(mesh, [frame_host.numpy()] * n, K, Ts).cpu().numpy(),
+                h2d=n * frame_host.numel() + n * (16 + 9) * 4, d2h=n * g * g * 4,
+                api="TrackingRefiner.pose_confidences(mesh, frames_host_u8, K, transforms) -> (n,37,37) confidences",
+                flops_per_unit=float(flops),
+                workload={"workload": f"smooth_poses_video refiner confidence pass (BASELINE configs[4]): {n} refinement "
+                                      "renders per frame, ViT-B/14-reg at 518^2 on the photo crop and on the render",
+                          "renders_per_frame": n, "crop": 518, "tokens": tokens, "mesh_faces": 20480,
+                          "l2": "activations of 2 x 64 x 1374 tokens ~1.6 GB >> 126 MB L2"})
+
+
+def setup_video(args, rank, world, dev):
+    """configs[3]: dino_inference_video on a 640x480 synthetic video with 8 proposals per frame: Proposals -> crop ->
+    DinoOnlinePoseEstimator.forward (coarse on the first frame, fine around prev_pose afterwards, reference
+    scripts/dino_inference_video.py:122-182).  Object tracks are dealt round-robin to the GPUs (one track per GPU at 8)."""
+    from freepose_b200 import cli, ops
+    from freepose_b200.pipeline.estimators.online_pose_estimator import DinoOnlinePoseEstimator
+    from freepose_b200.pipeline.proposals import Proposals
+    from freepose_b200.vit_weights import synthetic_state_dict
+    n_obj = 8
+    model = DinoOnlinePoseEstimator(n_coarse_poses=args.hyp, n_fine_poses=20000, cache_size=50,
+                                    cache_dir=f"/tmp/fp_bench_video_{rank}", resolution=args.res, chunk=args.hyp + 1,
+                                    weights=synthetic_state_dict(seed=0, depth=args.layer))
+    templates = cli.SyntheticTemplates(n_obj, args.hyp, args.res, crop=True, subdivisions=4)
+    mine = [j for j in range(n_obj) if j % world == rank]
+    meshes_r = {j: templates.mesh(j) for j in mine}
+    meshes_full = {j: meshes_r[j].copy().apply_scale(4.0) for j in mine}
+    entries = {j: templates[j] for j in mine}
+    # scene: the 8 objects on a 4 x 2 grid, 3 m away (K from the image diagonal, dino_inference_video.py:116-118)
+    h, w = 480, 640
+    f = float(np.sqrt(h ** 2 + w ** 2))
+    K = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]])
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 60, (h, w, 3), dtype=np.uint8)
+    boxes, masks = [], []
+    for j in range(n_obj):
+        qm, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(qm) < 0:
+            qm[:, 0] = -qm[:, 0]
+        pose = np.eye(4); pose[:3, :3] = qm
+        z = 3.0
+        pose[:3, 3] = [((80 + 160 * (j % 4)) - w / 2) * z / f, ((120 + 240 * (j // 4)) - h / 2) * z / f, z]
+        metric = templates.mesh(j).copy().apply_scale(4.0 * 0.3)
+        rgb, depth = ops.rasterize_mesh(metric, torch.from_numpy(pose[None]).float().to(dev), f, f, w / 2, h / 2, 640)
+        rgb, depth = rgb[0, :h, :w].cpu().numpy(), depth[0, :h, :w].cpu().numpy()
+        m = depth > 0
+        img[m] = rgb[m]
+        ys, xs = np.nonzero(m)
+        boxes.append([xs.min(), ys.min(), xs.max(), ys.max()])
+        masks.append(m)
+    boxes, masks = np.array(boxes), np.array(masks)
+    prev = {j: None for j in mine}
+    count = {"hyp": 0}
+
+    def step_e2e():
+        props = Proposals(img, {"boxes": torch.from_numpy(boxes), "masks": torch.from_numpy(masks)}, args.res,
+                          bbox_extend=0.05)
+        outs = []
+        for j in mine:
+            first = prev[j] is None
+            out = model(props.proposals[j], props.proposals_masks[j], entries[j], meshes_full[j], K,
+                        boxes[j].astype(np.float64), 0.3, prev_pose=prev[j], neighborhood=15, layer=args.layer,
+                        batch_size=128)
+            prev[j] = out["TCO"][0]
+            count["hyp"] += len(out["selected_poses"]) + (args.hyp if first else 0)
+            outs.append(out)
+        return outs
+
+    def reset():
+        for j in mine:
+            prev[j] = None
+        model.coarse_estimator.feature_cache.clear()
+        model.coarse_estimator._device_cache.clear()
+
+    return dict(metric=f"video frames/sec (8 proposals/frame, coarse->fine, crops @{args.res}^2)", unit="frames/s",
+                units_per_step=1.0 / world, step_device=None, step_e2e=step_e2e, counters=count, reset=reset,
+                h2d=img.size + masks.size + boxes.size * 4, d2h=len(mine) * (8 * 8 + 4 + 4),
+                api="Proposals(frame_host_u8, masks, boxes) + DinoOnlinePoseEstimator.forward(..., prev_pose) per proposal",
+                flops_per_unit=None,
+                workload={"workload": "dino_inference_video (BASELINE configs[3]): 640x480 synthetic frames, 8 proposals per "
+                                      f"frame, {args.hyp} coarse hypotheses on the first frame, then the fine poses within 15 "
+                                      "degrees of prev_pose out of 20000 (~19 per proposal), static scene",
+                          "proposals_per_frame": n_obj, "tracks_per_gpu": len(mine), "crop": args.res, "layer": args.layer,
+                          "l2": "per-call working set ~60 MB of activations (20 crops): fits L2; weights (554 MB) do not"})
+
+
+def run_secondary(args):
+    from freepose_b200 import _lib
+    from freepose_b200.distributed import init_from_env
+    import torch.distributed as dist
+    rank, local, world = init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU"
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    cfg = {"ffa": setup_ffa, "video": setup_video, "refiner": setup_refiner}[args.config](args, rank, world, dev)
+    step = cfg["step_device"] or cfg["step_e2e"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib.fp_profile_reset(); lib.fp_profile_enable(1)
+    launches0 = lib.fp_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if "counters" in cfg:
+        cfg["counters"]["hyp"] = 0
+    if "reset" in cfg:
+        cfg["reset"]()      # video: the timed frames start a NEW video (no previous poses, no cached template features)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    lib.fp_profile_enable(0)
+    launches = lib.fp_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    units = cfg["units_per_step"] * world * args.steps
+    value = units / (ms_total / 1e3)
+    kinds = {}
+    for k in range(lib.fp_profile_num_kinds()):
+        ms, work, n = C.c_double(), C.c_double(), C.c_longlong()
+        _lib.check(lib.fp_profile_collect(k, C.byref(ms), C.byref(work), C.byref(n)), "fp_profile_collect")
+        if n.value:
+            kinds[lib.fp_profile_kind_name(k).decode()] = (ms.value, work.value, n.value)
+    lib.fp_profile_reset()
+    hyp_timed = cfg.get("counters", {}).get("hyp")
+    # e2e with host buffers
+    for _ in range(2):
+        cfg["step_e2e"]()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cfg["step_e2e"]()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    if rank != 0:
+        return
+    pk = peaks()
+    tensor_kinds = {k for k in kinds if k.startswith("gemm") or k == "attention"}
+    total_kernel_ms = sum(v[0] for v in kinds.values())
+    breakdown = {}
+    for name, (ms, work, n) in sorted(kinds.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_step": ms / args.steps, "share": ms / total_kernel_ms, "launches_per_step": n / args.steps}
+        ent["tflops" if name in tensor_kinds else "gbs"] = work / ms / (1e9 if name in tensor_kinds else 1e6)
+        breakdown[name] = ent
+    dom = max(kinds, key=lambda k: kinds[k][0])
+    dms, dwork, dn = kinds[dom]
+    is_tensor = dom in tensor_kinds
+    achieved = dwork / dms / (1e9 if is_tensor else 1e6)
+    peak = pk["bf16_sustained"] if is_tensor else pk["hbm"]
+    out = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg["workload"], "clocks": clocks,
+           "value_includes_host_io": cfg["step_device"] is None,
+           "e2e": {"value": units / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": cfg["h2d"],
+                   "d2h_bytes_per_step": cfg["d2h"], "ms_per_step": 1e3 * e2e_s / args.steps, "api": cfg["api"]},
+           "gpu_launches": int(launches),
+           "roofline": {"kernel": dom, "bound": "tensor" if is_tensor else "hbm", "achieved": achieved, "peak": peak,
+                        "unit": "TFLOP/s" if is_tensor else "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": pk["source"], "avg_launch_ms": dms / dn},
+           "kernels": breakdown, "kernel_time_share_of_step": total_kernel_ms / args.steps / (ms_total / args.steps),
+           "cpu_baseline": None}
+    if cfg["flops_per_unit"]:
+        tf = value / world * cfg["flops_per_unit"] / 1e12
+        out["vit_flop_roofline"] = {"achieved_tflops_per_gpu": tf, "frac_of_sustained": tf / pk["bf16_sustained"]}
+    if hyp_timed is not None:
+        out["hypotheses_per_sec"] = hyp_timed * world / (ms_total / 1e3)
+        out["hypotheses_per_frame"] = hyp_timed * world / args.steps
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,11 +692,18 @@ def main():
     ap.add_argument("--chunk", type=int, default=521)
     ap.add_argument("--ref-hyp", type=int, default=8, help="hypotheses per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline and parity legs")
+    ap.add_argument("--config", default="pose", choices=["pose", "ffa", "video", "refiner"],
+                    help="pose = BASELINE configs[1] (the headline line); ffa / video / refiner = configs[2] / [3] / [4]")
+    ap.add_argument("--batch", type=int, default=None, help="ffa: renders per batch (256); refiner: renders per frame (64)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one proposal per GPU per step; strong: one proposal, hypotheses sharded over the GPUs")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 64 if args.config == "refiner" else 256
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "pose":
+        run_secondary(args)
     else:
         run_b200(args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

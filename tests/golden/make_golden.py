@@ -217,6 +217,65 @@ def golden_refiner():
     np.savez_compressed(OUT / "refiner.npz", **store)
 
 
+def online_fine_inputs(seed=21, n_views=6, res=420):
+    """Seeded inputs of the fine-stage fixture (regenerated identically by the tests: only outputs are stored)."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(1, 900, 1024, generator=g)
+    feats = (0.5 * q + 0.8 * torch.randn(n_views, 900, 1024, generator=g)).to(torch.bfloat16)
+    query = (q * (1.0 + 2.0 * torch.rand(1, 900, 1, generator=g))).to(torch.bfloat16)     # per-patch norms differ (raw query)
+    yy, xx = torch.meshgrid(torch.arange(res), torch.arange(res), indexing="ij")
+    tmasks = torch.stack([((yy - 210 - 9 * i) ** 2 / (60.0 + 9 * i) ** 2 + (xx - 200 + 7 * i) ** 2 / (90.0 - 5 * i) ** 2) < 1
+                          for i in range(n_views)])
+    pmask = ((yy - 180) ** 2 + (xx - 230) ** 2) < 100 ** 2
+    return feats, query, tmasks, pmask
+
+
+def golden_online_fine():
+    """Fine stage of the video path, the reference's own code (online_pose_estimator.py:26-34, 49-79):
+    * DinoOnlinePoseEstimator.geodesic_distance + np.where(dists < neighborhood) over the 20 000 fine poses for seeded
+      previous poses (executed from the imported reference class);
+    * the scoring lines 67-76 executed verbatim on CPU tensors: mask_scores with the (30, 30) bilinear resize of
+      OR(template masks, proposal mask), with a normalised query (frames > 0) and with the RAW coarse query feature
+      (first frame: online_pose_estimator.py:41,50 never normalises it)."""
+    import torch.nn.functional as F
+    from einops import einsum
+    ope = refimport.import_reference("src.pipeline.estimators.online_pose_estimator")
+    pe = refimport.import_reference("src.pipeline.estimators.pose_estimator")
+    fine = np.array(pe.DinoPoseEstimator.generate_poses(20000))
+    rng = np.random.default_rng(5)
+    prevs = []
+    for i in range(6):
+        qm, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(qm) < 0:
+            qm[:, 0] = -qm[:, 0]
+        T = np.eye(4); T[:3, :3] = qm; T[:3, 3] = rng.normal(size=3)
+        prevs.append(T)
+    prevs.append(fine[1234].copy())                       # exactly a fine pose: distance 0 to itself
+    store = {"prev_poses": np.array(prevs), "fine_sha": np.array(sha(fine))}
+    for i, T in enumerate(prevs):
+        d = ope.DinoOnlinePoseEstimator.geodesic_distance(fine[:, :3, :3], T)      # as called at line 55
+        for nb in (15, 5):
+            close = np.where(d < nb)[0]
+            store[f"close_{i}_{nb}"] = close.astype(np.int32)
+        store[f"dist_{i}"] = d[store[f"close_{i}_15"]]
+    # ---- scoring lines, verbatim
+    feats_fine_template, query_raw, masks_fine_template, proposal_mask = online_fine_inputs()
+    signature = 'b n d, b n d -> b n'
+    for tag, query_feat in (("norm", F.normalize(query_raw, dim=-1)), ("raw", query_raw)):
+        scores = einsum(query_feat, F.normalize(feats_fine_template, dim=-1), signature)
+        masks = torch.logical_or(masks_fine_template, proposal_mask[None]).to(torch.float16)
+        n_views = feats_fine_template.shape[0]
+        masks = F.interpolate(masks[None].float(), size=(30, 30), mode='bilinear').reshape(n_views, 900)
+        scores_m = (scores * masks).sum(dim=-1) / masks.sum(dim=-1)
+        scores_u = einsum(query_feat, F.normalize(feats_fine_template, dim=-1), signature).mean(dim=-1)
+        store[f"masked_{tag}"] = scores_m.float().numpy()
+        store[f"plain_{tag}"] = scores_u.float().numpy()
+        store[f"argmax_masked_{tag}"] = torch.argmax(scores_m).numpy()
+        store[f"argmax_plain_{tag}"] = torch.argmax(scores_u).numpy()
+    store["weights"] = masks.numpy()
+    np.savez_compressed(OUT / "online_fine.npz", **store)
+
+
 def template_store_case(n_views):
     """Seeded renders for the template-store fixture (shared with tests/test_template_store.py)."""
     from freepose_b200.pipeline.utils import generate_poses
@@ -266,5 +325,6 @@ if __name__ == "__main__":
     golden_retrieval()
     golden_refiner()
     golden_template_store()
+    golden_online_fine()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -242,6 +242,33 @@ def test_score_golden_ties_weights_and_raw_query(ops, golden):
     assert np.array_equal(sr.cpu().numpy(), S.engine_order_scores(ft, fq, normalise_query=False))
 
 
+def test_score_fine_stage_masked_and_raw_query_vs_reference_lines(ops, golden):
+    """Fine stage (online_pose_estimator.py:67-79): mask-weighted score with the (30, 30) bilinear resize of
+    OR(template mask, proposal mask), for a normalised query (frames > 0) and for the RAW coarse query feature (first
+    frame).  Expected values: the reference's lines executed verbatim on the CPU (tests/golden/online_fine.npz); the
+    inputs are regenerated from the same seeds."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    from make_golden import online_fine_inputs
+    import torch.nn.functional as F
+    g = golden["online_fine"]
+    feats, query, tmasks, pmask = online_fine_inputs()
+    # the estimator's own weight computation (pipeline/estimators/online_pose_estimator.py forward_fine), on the device
+    mk = torch.logical_or(tmasks.to(dev), pmask.to(dev)[None]).float()
+    weights = F.interpolate(mk[None], size=(30, 30), mode="bilinear")[0].reshape(len(feats), 900).contiguous()
+    np.testing.assert_allclose(weights.cpu().numpy(), g["weights"], rtol=0, atol=1e-6)
+    for tag, normalise in (("norm", True), ("raw", False)):
+        sm, im, _, _ = ops.score_topk(feats.to(dev), query.to(dev), k=1, weights=weights, normalise_query=normalise)
+        np.testing.assert_allclose(sm.cpu().numpy(), g[f"masked_{tag}"], rtol=3e-6)
+        assert int(im) == int(g[f"argmax_masked_{tag}"])
+        su, iu, _, _ = ops.score_topk(feats.to(dev), query.to(dev), k=1, normalise_query=normalise)
+        ref = g[f"plain_{tag}"]
+        ulp = 2.0 ** (np.floor(np.log2(np.abs(ref))) - 7)
+        assert np.all(np.abs(su.cpu().numpy() - ref) <= ulp)                  # bf16-valued: at most one ulp (summation order)
+        assert ref[int(iu)] >= ref.max() - ulp[int(iu)]
+
+
 def test_score_full_size_properties(ops):
     """BASELINE size (520 x 256 x 1024): permutation equivariance, power-of-two scale invariance, determinism."""
     ft, fq = _score_case(520, 256, 5)

@@ -301,3 +301,20 @@ def test_raster_oracle_clips_at_the_near_plane_like_an_analytic_ray_caster():
     W = np.array([[-400, -0.5, 1.0], [0.2, -0.5, 2.0], [0.2, 0.2, 2.0], [-400, 0.2, 1.0]], np.float32)
     _, dw = R.render(W, F, col, np.eye(4)[None], f, f, c, c, res, msaa=1)
     assert (dw[0, 40:60, :20] > 0).all() and not (dw[0, :10, :] > 0).any()
+
+
+def test_fine_stage_neighbourhood_matches_reference(golden):
+    """online_pose_estimator.py:26-34,55-56: geodesic distance of the 20 000 fine poses to the previous pose and the
+    `dists < neighborhood` selection -- index sets minted by the reference's own static method (scipy rotvec norm); the
+    product computes the same angle in closed form (atan2 of the skew part and the trace)."""
+    from freepose_b200.pipeline.estimators.online_pose_estimator import DinoOnlinePoseEstimator
+    from freepose_b200.pipeline.utils import generate_poses
+    g = golden["online_fine"]
+    fine = np.array(generate_poses(20000))
+    assert hashlib.sha256(np.ascontiguousarray(fine).tobytes()).hexdigest() == str(g["fine_sha"])
+    for i, T in enumerate(g["prev_poses"]):
+        d = DinoOnlinePoseEstimator.geodesic_distance(fine, T)
+        for nb in (15, 5):
+            assert np.array_equal(np.where(d < nb)[0], g[f"close_{i}_{nb}"]), (i, nb)
+        np.testing.assert_allclose(d[g[f"close_{i}_15"]], g[f"dist_{i}"], rtol=0, atol=1e-6)
+    assert 1234 in g["close_6_5"] and len(g["close_1_5"]) == 0        # a fine pose finds itself; 5 degrees can be empty

@@ -115,3 +115,30 @@ def test_split_key_contract_is_as_accurate_as_single_pass():
         assert torch.equal(split[..., 256:, :], single[..., 256:, :])        # leftover rows: the same single pass
     # dispatch: 261 tokens -> split, everything else unchanged
     assert torch.equal(contract_attention(q, k, v, 0.125), contract_attention_split(q, k, v, 0.125))
+
+
+def test_video_path_autocast_arithmetic_delta_is_one_score_ulp():
+    """The reference's VIDEO script feeds `.half()` crops under torch.autocast(bf16) (dino_inference_video.py:151,
+    online_pose_estimator.py:51,66); its static script feeds bf16 crops to the bf16 model (dino_inference.py) -- the
+    arithmetic the engine implements.  Measured here with the reference's own DINOv2FeatureExtractor.forward around the
+    oracle ViT (CPU autocast): the two arithmetics differ by ~1e-2 relative in the layer-22 tokens (the same order as
+    any re-ordering of the bf16 contract, see CONTRACT_DRIFT_FP32_VS_FP64) and by at most ONE bf16 ulp in the pose
+    scores, with the same argmax.  So the engine does not carry a second, autocast-flavoured code path."""
+    from oracle import refimport, score as oscore
+    if not refimport.available():
+        pytest.skip("/root/reference not present")
+    sd22 = synthetic_state_dict(seed=0, depth=22)
+    g = torch.Generator().manual_seed(3)
+    base = torch.rand(1, 3, 224, 224, generator=g)
+    x = (base + 0.15 * torch.randn(6, 3, 224, 224, generator=g)).clamp(0, 1)      # 5 "renders" + 1 "query", correlated
+    fe = refimport.reference_feature_extractor(OracleViT(sd22).to(torch.bfloat16))
+    with torch.no_grad():
+        fa = fe(x.to(torch.bfloat16), layer=22, feature_type="patch")
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            fb = fe(x.half(), layer=22, feature_type="patch")
+    assert 1e-3 < rel_l2(fb, fa) < 3e-2
+    sa = oscore.reference_scores(fa[:-1].to(torch.bfloat16), fa[-1:].to(torch.bfloat16)).float()
+    sb = oscore.reference_scores(fb[:-1].to(torch.bfloat16), fb[-1:].to(torch.bfloat16)).float()
+    ulp = 2.0 ** (torch.floor(torch.log2(sa.abs())) - 7)
+    assert torch.all((sa - sb).abs() <= ulp), (sa, sb)
+    assert int(sa.argmax()) == int(sb.argmax())
