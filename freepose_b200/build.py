@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 LIB = PKG / "libfreepose_b200.so"
 
-SOURCES = ["common.cu", "gemm.cu", "attention.cu", "attention_long.cu", "attention_split.cu", "elementwise.cu", "score.cu", "retrieval.cu", "raster.cu", "geometry.cu", "refiner.cu", "comm.cu",
+SOURCES = ["common.cu", "gemm.cu", "attention.cu", "attention_long.cu", "attention_split.cu", "attention_pair.cu", "elementwise.cu", "score.cu", "retrieval.cu", "raster.cu", "geometry.cu", "refiner.cu", "comm.cu",
            "vit.cu", "capi.cu"]
 
 NVCC_FLAGS = [

@@ -656,7 +656,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream) {
   FP_REQUIRE(B > 0 && H > 0 && T > 0, "attention: empty problem");
   const int tpad = (T + 15) / 16 * 16;
-  if (tpad > MAX_TPAD) return attention_long_bf16(qkv, out, B, T, H, scale, stream);  // crops above 224^2
+  if (tpad > MAX_TPAD) {   // crops above 224^2
+    static const int v1 = [] { const char* e = getenv("FP_ATTN_LONG_V1"); return e ? atoi(e) : 0; }();
+    return v1 ? attention_long_bf16(qkv, out, B, T, H, scale, stream) : attention_pair_bf16(qkv, out, B, T, H, scale, stream);
+  }
   {
     // 224^2 crops: the two-stream kernel.  FP_ATTN_SPLIT=0 selects the single-stream kernel below (A/B measurements);
     // FP_ATTN_POLY=0x1111 / 0x5555 moves 25 / 50 % of the exponentials to the FMA pipe.

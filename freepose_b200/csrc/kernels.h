@@ -40,6 +40,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 // to attention_long_bf16: key blocks of 256 with an online softmax (oracle: contract_attention(key_block=256)).
 int attention_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
 int attention_long_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
+// T > 272: two query tiles in flight, key blocks of 96, double-buffered logits (attention_pair.cu; oracle:
+// contract_attention(key_block=96)).  attention_long_bf16 is its predecessor (key blocks of 256), kept for A/B runs.
+int attention_pair_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, cudaStream_t stream);
 // T == 261 (224^2 crops): two independent key streams per query tile (attention_split.cu)
 int attention_split_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float scale, unsigned poly_mask,
                          cudaStream_t stream);

@@ -152,7 +152,7 @@ def contract_layernorm(x, w, b, eps):
 
 
 SINGLE_PASS_KEYS = 272   # padded keys the single-pass kernel holds in TMEM (freepose_b200/csrc/attention.cu)
-KEY_BLOCK = 256          # key block of the tiled-key kernel (freepose_b200/csrc/attention_long.cu)
+KEY_BLOCK = 96           # key block of the tiled-key kernel (freepose_b200/csrc/attention_pair.cu)
 
 
 SPLIT_TOKENS = 261       # 224^2 crops: the two-stream kernel (freepose_b200/csrc/attention_split.cu)
