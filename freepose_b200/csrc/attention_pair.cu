@@ -30,8 +30,8 @@
 //
 // TMEM (512 columns): S[stream][buffer] 4 x 96, O[stream] 2 x 64.
 // Work item = (image, head, pair of query tiles).  Arithmetic contract: oracle/vit.py contract_attention with
-// key_block = 96 -- block-wise flash attention: P of block j is exp2((s - m_j) c) rounded to bf16, m_j the running max
-// after block j.
+// key_block = 96, lazy_tau = 8 -- block-wise flash attention: P of block j is exp2((s - m_j) c) rounded to bf16, m_j the
+// row's reference maximum after block j (the running maximum, updated lazily: see LAZY_TAU).
 #include <stdlib.h>
 
 #include "attention_common.cuh"
@@ -54,6 +54,7 @@ constexpr int NUM_THREADS = 384;
 constexpr int TMEM_COLS = 512;
 constexpr int O_COL = 4 * KB;                 // 384
 constexpr int NGROUPS = KB / 32;              // 3 groups of 32 keys = P chunks
+constexpr float LAZY_TAU = 8.0f;              // log2 of the largest un-normalised P before the reference max moves
 
 constexpr int OFF_Q = 0;                                   // [2 streams][2 slots]
 constexpr int OFF_K = OFF_Q + 4 * Q_TILE_BYTES;
@@ -330,16 +331,24 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             m = max_group<true>(s2, valid - 64, m);
           }
         }
-        const float m_new = fmaxf(m_run, m);
-        const float alpha = ex2((m_run - m_new) * p.sl2);  // 0 for the first block (m_run = -inf)
+        // LAZY reference maximum (the FlashAttention-4 rule): the row's reference m_run moves (and O / l are rescaled) only
+        // when the block maximum exceeds it by more than 2^LAZY_TAU in the exponent; until then P = exp2((s - m_run) c) may
+        // reach 2^LAZY_TAU instead of 1 -- the same relative bf16 precision, and O / l at the end does not care which
+        // reference the sums were taken against.  Rescaling needs the previous P.V to have COMPLETED, a stall of a few
+        // hundred cycles per block on the softmax warps' critical path; with the threshold it is paid a few times per row
+        // instead of in almost every block (32 rows per warp: some row raises its maximum in nearly every block).
+        const bool grow = (m - m_run) * p.sl2 > LAZY_TAU;      // true for the first block (m_run = -inf)
+        const float m_new = grow ? m : m_run;
+        const float alpha = grow ? ex2((m_run - m_new) * p.sl2) : 1.0f;   // 0 for the first block
         const float msl = m_new * p.sl2;
-        // ---- O slot: rescale by alpha (kb > 0) or hand the previous item over to HBM (kb == 0); either way the previous
-        //      P.V has had the whole max pass to finish
-        if (j > 0) {
+        const bool rescale = kb > 0 && warp_active && __any_sync(0xffffffffu, grow);
+        // ---- O slot: rescale by alpha (kb > 0, only when a row of this warp moved its reference) or hand the previous
+        //      item over to HBM (kb == 0)
+        if (j > 0 && (kb == 0 || rescale)) {
           mbar_wait(&o_full[st], (j - 1) & 1);
           tc_fence_after();
           if (kb > 0) {
-            if (warp_active && __any_sync(0xffffffffu, alpha != 1.0f)) {
+            {
 #pragma unroll
               for (int hx = 0; hx < 2; ++hx) {
                 uint32_t o[32];

@@ -189,13 +189,17 @@ def contract_attention_split(q, k, v, scale, split=SPLIT_KEYS, tile=128):
     return rb(out)
 
 
-def contract_attention(q, k, v, scale, key_block=None):
+LAZY_TAU = 8.0           # attention_pair.cu: log2 of the largest un-normalised P before a row's reference max moves
+
+
+def contract_attention(q, k, v, scale, key_block=None, lazy_tau=LAZY_TAU):
     """Flash/xformers-style attention on bf16-valued fp32 tensors (B, H, N, hd).
 
     261 tokens (224^2 crops, the headline shape) run the two-stream form (contract_attention_split).  Otherwise, up to
     SINGLE_PASS_KEYS keys the softmax is a single pass; above that (crops larger than 224^2) it is the
     block-wise online softmax of flash attention with KEY_BLOCK keys per block: the bf16 P of block b is taken
-    against the running max after block b, and O / l are rescaled by exp(m_old - m_new) between blocks.
+    against the row's reference max after block b (the running max, moved lazily: FlashAttention-4's rule), and O / l
+    are rescaled by exp(m_old - m_new) when it moves.
     """
     N = k.shape[-2]
     if key_block is None and N == SPLIT_TOKENS:
@@ -212,10 +216,15 @@ def contract_attention(q, k, v, scale, key_block=None):
     m = torch.full(q.shape[:-1] + (1,), float("-inf"), dtype=q.dtype)
     l = torch.zeros_like(m)
     o = torch.zeros_like(q)
+    log2e = 1.4426950408889634
     for k0 in range(0, N, key_block):
         s = (q @ k[..., k0:k0 + key_block, :].transpose(-2, -1)) * scale
-        m_new = torch.maximum(m, s.amax(dim=-1, keepdim=True))
-        alpha = torch.exp(m - m_new)                      # 0 for the first block
+        blk = s.amax(dim=-1, keepdim=True)
+        # lazy reference maximum (attention_pair.cu LAZY_TAU): it moves only when the block maximum exceeds it by more
+        # than 2^lazy_tau in the exponent; lazy_tau = 0 is the classic running maximum
+        grow = (blk - m) * log2e > lazy_tau
+        m_new = torch.where(grow, blk, m)
+        alpha = torch.where(grow, torch.exp(m - m_new), torch.ones_like(m))   # 0 for the first block
         p = torch.exp(s - m_new)
         l = l * alpha + p.sum(dim=-1, keepdim=True)
         o = o * alpha + rb(p) @ v[..., k0:k0 + key_block, :]

@@ -142,3 +142,19 @@ def test_video_path_autocast_arithmetic_delta_is_one_score_ulp():
     ulp = 2.0 ** (torch.floor(torch.log2(sa.abs())) - 7)
     assert torch.all((sa - sb).abs() <= ulp), (sa, sb)
     assert int(sa.argmax()) == int(sb.argmax())
+
+
+def test_lazy_reference_max_contract_is_as_accurate_as_the_running_max():
+    """attention_pair.cu moves a row's reference maximum only when a block exceeds it by more than 2^8 in the exponent
+    (FlashAttention-4's lazy rescale).  Against exact (fp64) softmax attention, that contract and the classic running-max
+    contract are equally far (905 tokens, flat and peaked softmaxes), and stay finite."""
+    from oracle.vit import contract_attention
+    torch.manual_seed(0)
+    for gain in (1.0, 4.0):
+        q, k, v = [(torch.randn(1, 3, 905, 64) * (gain if i < 2 else 1)).to(torch.bfloat16).float() for i in range(3)]
+        exact = (torch.softmax((q.double() @ k.double().transpose(-2, -1)) * 0.125, -1) @ v.double())
+        lazy = contract_attention(q, k, v, 0.125).double()
+        classic = contract_attention(q, k, v, 0.125, lazy_tau=0.0).double()
+        e_lazy = ((lazy - exact).norm() / exact.norm()).item()
+        e_classic = ((classic - exact).norm() / exact.norm()).item()
+        assert torch.isfinite(lazy).all() and e_lazy < 1.25 * e_classic and e_lazy < 3e-3, (gain, e_lazy, e_classic)
