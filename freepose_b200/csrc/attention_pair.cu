@@ -300,6 +300,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // ---- pass 1: block row max
         mbar_wait(&s_full[st * 2 + buf], (j >> 1) & 1);
         tc_fence_after();
+        // The four warps of a stream share the count-4 barriers o_ready / p_full, one phase per block: a warp may only
+        // arrive for block j once all four have arrived for block j-1.  (Waiting for P.V(j-1) used to imply that; with the
+        // lazy rescale nothing else does.)
+        named_bar_sync(1 + st, 128);
         if (warp_active) {
           if (full_block) {
             tmem_ld_32x32b_x32(sbase, s0);
