@@ -348,6 +348,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool rescale = kb > 0 && warp_active && __any_sync(0xffffffffu, grow);
         // ---- O slot: rescale by alpha (kb > 0, only when a row of this warp moved its reference) or hand the previous
         //      item over to HBM (kb == 0)
+        // A parity wait is only meaningful within one phase of the barrier: observe P.V(j-2) in EVERY block (it completed
+        // long ago: no stall), so that a later wait for P.V(j-1) can never be two phases off after skipped blocks.
+        if (j > 1) mbar_wait(&o_full[st], (j - 2) & 1);
         if (j > 0 && (kb == 0 || rescale)) {
           mbar_wait(&o_full[st], (j - 1) & 1);
           tc_fence_after();
