@@ -87,9 +87,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* q_empty = bars + 22;      // [2][2]
   uint64_t* s_full = bars + 26;       // [2 streams][2 buffers]
   uint64_t* p_full = bars + 30;       // [2 streams][3 groups]  (4 arrivals: the stream's warps)
-  uint64_t* o_full = bars + 36;       // [2]  P.V of a key block complete
-  uint64_t* o_ready = bars + 38;      // [2]  O rescaled / read out: this block's P.V may accumulate (4 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 40);
+  // [2 streams][2]: P.V of key block j complete, on barrier j & 1.  Two barriers per stream because the softmax warps wait
+  // for it only when they have to rescale O: a parity wait is meaningful only within one phase of its barrier, and with
+  // alternating barriers "block j-1" is always either the pending or the last completed phase of its barrier (S of block
+  // j, which the warp has just waited for, was issued behind P.V of block j-2).
+  uint64_t* o_full = bars + 36;
+  uint64_t* o_ready = bars + 40;      // [2]  O rescaled / read out: this block's P.V may accumulate (4 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 42);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = p.B * p.H * p.npq;
@@ -105,7 +109,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
     for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); }
     for (int i = 0; i < 6; ++i) mbar_init(&p_full[i], 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_ready[i], 4); }
+    for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&o_ready[i], 4);
     fence_barrier_init();
   }
   if (warp == 3) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -207,7 +212,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                            (kb | key0) != 0);
           }
         }
-        umma_commit(&o_full[st]);
+        umma_commit(&o_full[st * 2 + (j & 1)]);
         umma_commit(&v_empty[vs]);
         if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
         if (++kb == p.nkb) kb = 0;
@@ -348,11 +353,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool rescale = kb > 0 && warp_active && __any_sync(0xffffffffu, grow);
         // ---- O slot: rescale by alpha (kb > 0, only when a row of this warp moved its reference) or hand the previous
         //      item over to HBM (kb == 0)
-        // A parity wait is only meaningful within one phase of the barrier: observe P.V(j-2) in EVERY block (it completed
-        // long ago: no stall), so that a later wait for P.V(j-1) can never be two phases off after skipped blocks.
-        if (j > 1) mbar_wait(&o_full[st], (j - 2) & 1);
         if (j > 0 && (kb == 0 || rescale)) {
-          mbar_wait(&o_full[st], (j - 1) & 1);
+          mbar_wait(&o_full[st * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc_fence_after();
           if (kb > 0) {
             {
@@ -418,7 +420,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       prev_l = l_run; prev_b = b; prev_h = h; prev_t = t;
     }
     if (j > 0) {
-      mbar_wait(&o_full[st], (j - 1) & 1);
+      mbar_wait(&o_full[st * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
       tc_fence_after();
       store_item(prev_b, prev_h, prev_t, prev_l);
     }
