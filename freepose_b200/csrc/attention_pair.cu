@@ -86,14 +86,19 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* q_full = bars + 18;       // [2 streams][2 slots]
   uint64_t* q_empty = bars + 22;      // [2][2]
   uint64_t* s_full = bars + 26;       // [2 streams][2 buffers]
-  uint64_t* p_full = bars + 30;       // [2 streams][3 groups]  (4 arrivals: the stream's warps)
+  // Every barrier between a stream's softmax warps and its issuer exists TWICE, alternating with the block parity: a
+  // parity wait is only meaningful within one phase of its barrier, and with the lazy rescale the softmax warps no
+  // longer wait for P.V(j-1), so they (or, for rows past the end of the image, which have nothing to compute, certainly)
+  // can be two blocks ahead of the issuer.  With alternating barriers the arrivals for block j+2 come behind S(j+2),
+  // which the issuer only issues after it has consumed the barriers of block j.
+  uint64_t* p_full = bars + 30;       // [2 streams][2 parities][3 groups]  (4 arrivals: the stream's warps)
   // [2 streams][2]: P.V of key block j complete, on barrier j & 1.  Two barriers per stream because the softmax warps wait
   // for it only when they have to rescale O: a parity wait is meaningful only within one phase of its barrier, and with
   // alternating barriers "block j-1" is always either the pending or the last completed phase of its barrier (S of block
   // j, which the warp has just waited for, was issued behind P.V of block j-2).
-  uint64_t* o_full = bars + 36;
-  uint64_t* o_ready = bars + 40;      // [2]  O rescaled / read out: this block's P.V may accumulate (4 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 42);
+  uint64_t* o_full = bars + 42;
+  uint64_t* o_ready = bars + 46;      // [2 streams][2 parities]  O rescaled / read out: this block's P.V may accumulate (4 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 50);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = p.B * p.H * p.npq;
@@ -108,9 +113,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < K_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
     for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
     for (int i = 0; i < 4; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); }
-    for (int i = 0; i < 6; ++i) mbar_init(&p_full[i], 4);
-    for (int i = 0; i < 4; ++i) mbar_init(&o_full[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&o_ready[i], 4);
+    for (int i = 0; i < 12; ++i) mbar_init(&p_full[i], 4);
+    for (int i = 0; i < 4; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_ready[i], 4); }
     fence_barrier_init();
   }
   if (warp == 3) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -198,11 +202,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint64_t v_desc = v_desc0 + uint64_t(vs * (KV_BLOCK_BYTES >> 4));
         const uint32_t p_tmem = s_tmem0 + (j & 1) * KB;
         mbar_wait(&v_full[vs], vphase);
-        mbar_wait(&o_ready[st], j & 1);        // O rescaled for this block's running max (or read out by the previous item)
+        mbar_wait(&o_ready[st * 2 + (j & 1)], (j >> 1) & 1);   // O rescaled for this block's reference max (or read out by the previous item)
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < NGROUPS; ++g) {
-          mbar_wait(&p_full[st * 3 + g], j & 1);   // (every group barrier completes one phase per block, keys or not)
+          mbar_wait(&p_full[(st * 2 + (j & 1)) * 3 + g], (j >> 1) & 1);   // (every group barrier completes one phase per use, keys or not)
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -280,11 +284,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     };
     // P of a group is published one group late: its tcgen05.st completes under the next group's exponentials
-    auto publish = [&](int g) {
+    auto publish = [&](uint32_t jj, int g) {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[st * 3 + g]);
+      if (lane == 0) mbar_arrive(&p_full[(st * 2 + (jj & 1)) * 3 + g]);
     };
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -305,10 +309,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // ---- pass 1: block row max
         mbar_wait(&s_full[st * 2 + buf], (j >> 1) & 1);
         tc_fence_after();
-        // The four warps of a stream share the count-4 barriers o_ready / p_full, one phase per block: a warp may only
-        // arrive for block j once all four have arrived for block j-1.  (Waiting for P.V(j-1) used to imply that; with the
-        // lazy rescale nothing else does.)
-        named_bar_sync(1 + st, 128);
         if (warp_active) {
           if (full_block) {
             tmem_ld_32x32b_x32(sbase, s0);
@@ -376,7 +376,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&o_ready[st]);
+        if (lane == 0) mbar_arrive(&o_ready[st * 2 + (j & 1)]);
         // ---- pass 2: exponentials against the running max, row sum, bf16 P into TMEM over the consumed logits
         float l = 0.f;
         uint32_t pk[16];
@@ -386,18 +386,18 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
-            for (int g = 0; g < NGROUPS; ++g) mbar_arrive(&p_full[st * 3 + g]);
+            for (int g = 0; g < NGROUPS; ++g) mbar_arrive(&p_full[(st * 2 + (j & 1)) * 3 + g]);
           }
         } else if (full_block) {
           l += exp_group<false>(s0, p.sl2, msl, 32, pk);
           tmem_st_32x32b_x16(sbase, pk);
           l += exp_group<false>(s1, p.sl2, msl, 32, pk);
-          publish(0);
+          publish(j, 0);
           tmem_st_32x32b_x16(sbase + 32, pk);
           l += exp_group<false>(s2, p.sl2, msl, 32, pk);
-          publish(1);
+          publish(j, 1);
           tmem_st_32x32b_x16(sbase + 64, pk);
-          publish(2);
+          publish(j, 2);
         } else {
 #pragma unroll
           for (int g = 0; g < NGROUPS; ++g) {
@@ -411,7 +411,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tmem_st_32x32b_x8(sbase + c0, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
               }
             }
-            publish(g);   // (also for a group without keys: its barrier completes one phase per block)
+            publish(j, g);   // (also for a group without keys: its barrier completes one phase per use)
           }
         }
         l_run = l_run * alpha + l;
