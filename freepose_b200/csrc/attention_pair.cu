@@ -73,6 +73,7 @@ struct Params {
   float sl2;  // scale * log2(e)
 };
 
+template <unsigned POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const __grid_constant__ CUtensorMap tmOut, const Params p) {
@@ -389,12 +390,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int g = 0; g < NGROUPS; ++g) mbar_arrive(&p_full[(st * 2 + (j & 1)) * 3 + g]);
           }
         } else if (full_block) {
-          l += exp_group<false>(s0, p.sl2, msl, 32, pk);
+          l += exp_group<false, POLY>(s0, p.sl2, msl, 32, pk);
           tmem_st_32x32b_x16(sbase, pk);
-          l += exp_group<false>(s1, p.sl2, msl, 32, pk);
+          l += exp_group<false, POLY>(s1, p.sl2, msl, 32, pk);
           publish(j, 0);
           tmem_st_32x32b_x16(sbase + 32, pk);
-          l += exp_group<false>(s2, p.sl2, msl, 32, pk);
+          l += exp_group<false, POLY>(s2, p.sl2, msl, 32, pk);
           publish(j, 1);
           tmem_st_32x32b_x16(sbase + 64, pk);
           publish(j, 2);
@@ -451,11 +452,24 @@ int attention_pair_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float s
   p.npq = (p.nq + 1) / 2;
   p.nkb = (tpad + KB - 1) / KB;
   p.sl2 = scale * 1.4426950408889634f;
-  FP_ENSURE_DYN_SMEM(attention_pair_kernel, SMEM_BYTES);
   const long long nitems = (long long)B * H * p.npq;
   const int grid = nitems < sm_count() ? int(nitems) : sm_count();
   ProfScope prof(PROF_ATTENTION, 4.0 * double(B) * H * double(T) * T * HD, 1, stream);
-  attention_pair_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmOut, p);
+  // FP_ATTN_POLY=0x1111 / 0x5555: 25 / 50 % of the exponentials on the FMA pipe (degree-4 polynomial) instead of the MUFU
+  static const unsigned poly = [] { const char* e = getenv("FP_ATTN_POLY"); return e ? unsigned(strtoul(e, nullptr, 0)) : 0u; }();
+#define FP_LAUNCH_PAIR(MASK_)                                                           \
+  do {                                                                                  \
+    auto kern = attention_pair_kernel<MASK_>;                                           \
+    FP_ENSURE_DYN_SMEM(kern, SMEM_BYTES);                                               \
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmOut, p);               \
+  } while (0)
+  switch (poly) {
+    case 0x1111u: FP_LAUNCH_PAIR(0x1111u); break;
+    case 0x5555u: FP_LAUNCH_PAIR(0x5555u); break;
+    case 0x0101u: FP_LAUNCH_PAIR(0x0101u); break;
+    default: FP_LAUNCH_PAIR(0u); break;
+  }
+#undef FP_LAUNCH_PAIR
   FP_CUDA(cudaGetLastError());
   return 0;
 }
