@@ -561,9 +561,12 @@ __device__ __noinline__ void hard_attributes(const Camera& cam, int b, int res, 
   }
 }
 
-template <int MODE>
+// WITH_HARD = false: the common path (resolve_kernel).  A hard triangle -- which only resolve_hard_kernel can shade --
+// yields black there and is overwritten afterwards; keeping that branch out of the common kernel keeps it at 48
+// registers without a stack frame (with it: 104 registers + 256 B of local memory, +1.6 ms per 521 views).
+template <int MODE, bool WITH_HARD>
 __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, const int* __restrict__ faces,
-                                      const Surface& sf, const Camera& cam, int b, int res, unsigned face, int px, int py,
+                                      const Surface& sf, const Camera* cam, int b, int res, unsigned face, int px, int py,
                                       int out[3]) {
   const int i0 = faces[3 * face], i1 = faces[3 * face + 1], i2 = faces[3 * face + 2];
   ScreenVertex v0 = svb[i0], v1 = svb[i1], v2 = svb[i2];
@@ -571,8 +574,9 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   const bool hard = v0.x == INT_MIN || v1.x == INT_MIN || v2.x == INT_MIN;
   float h_vc[3], h_uvd[6];   // (only written and read on the hard path)
   if (hard) {
+    if (!WITH_HARD) { out[0] = out[1] = out[2] = 0; return; }
     h_vc[0] = h_vc[1] = h_vc[2] = 255.f;
-    hard_attributes(cam, b, res, sf, i0, i1, i2, px, py, MODE == 0 || sf.colors != nullptr, MODE == 1, h_vc, h_uvd);
+    hard_attributes(*cam, b, res, sf, i0, i1, i2, px, py, MODE == 0 || sf.colors != nullptr, MODE == 1, h_vc, h_uvd);
   }
   long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
   if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
@@ -594,7 +598,7 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   float w0, w1, w2, wsum;
   weights(sx, sy, w0, w1, w2, wsum);
   float vc[3] = {255.f, 255.f, 255.f};
-  if (hard) {
+  if (WITH_HARD && hard) {
     vc[0] = h_vc[0]; vc[1] = h_vc[1]; vc[2] = h_vc[2];
   } else if (MODE == 0 || sf.colors != nullptr) {
 #pragma unroll
@@ -620,7 +624,7 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   float dvx = __fmul_rn(__fadd_rn(interp(x0w, x1w, x2w, xs, va, vb, vcc), -v), fh);
   float duy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, ua, ub, uc), -u), fw);
   float dvy = __fmul_rn(__fadd_rn(interp(y0w, y1w, y2w, ys, va, vb, vcc), -v), fh);
-  if (hard) { u = h_uvd[0]; v = h_uvd[1]; dux = h_uvd[2]; dvx = h_uvd[3]; duy = h_uvd[4]; dvy = h_uvd[5]; }
+  if (WITH_HARD && hard) { u = h_uvd[0]; v = h_uvd[1]; dux = h_uvd[2]; dvx = h_uvd[3]; duy = h_uvd[4]; dvy = h_uvd[5]; }
   const float rx = __fadd_rn(__fmul_rn(dux, dux), __fmul_rn(dvx, dvx));
   const float ry = __fadd_rn(__fmul_rn(duy, duy), __fmul_rn(dvy, dvy));
   const float lod = lod_from_rho2(fmaxf(rx, ry), sf.tex_levels);
@@ -653,8 +657,8 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
 template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
-               const int* __restrict__ faces, const Surface sf, const Camera cam, uint8_t* __restrict__ rgb,
-               float* __restrict__ depth, int V, int res) {
+               const int* __restrict__ faces, const Surface sf, uint8_t* __restrict__ rgb, float* __restrict__ depth,
+               int V, int res) {
   const int b = blockIdx.y;
   const int npix = res * res;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,7 +692,7 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
             for (int ch = 0; ch < 3; ++ch)
               col[ch] = to_unorm8(__fmul_rn(float(sf.colors[3 * face + ch]), sf.ambient_255), sf.gamma_lut);
           } else {
-            shade<MODE>(svb, faces, sf, cam, b, res, face, px, py, col);
+            shade<MODE, false>(svb, faces, sf, nullptr, b, res, face, px, py, col);
           }
           last_face = face;
         }
@@ -712,6 +716,52 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
   }
 }
 
+// Second resolve pass for the views flagged by the vertex kernel: pixels with at least one sample won by a hard triangle
+// are shaded again (hard triangles through hard_attributes, the others as before) and their RGB overwritten.  Depth is
+// already final.  Views without such vertices return at once.
+template <int S, int MODE>
+__global__ void __launch_bounds__(256)
+resolve_hard_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
+                    const int* __restrict__ faces, const Surface sf, const Camera cam, const int* __restrict__ view_hard,
+                    uint8_t* __restrict__ rgb, int V, int res) {
+  const int b = blockIdx.y;
+  if (!view_hard[b]) return;
+  const int npix = res * res;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int py = p / res, px = p - py * res;
+  const ScreenVertex* svb = sv + size_t(b) * V;
+  const unsigned long long* kv = keys + (size_t(b) * npix + p) * S;
+  bool any_hard = false;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const unsigned long long k = kv[s];
+    if (k != ~0ull) {
+      const unsigned face = unsigned(k & 0xffffffffu);
+      any_hard |= svb[faces[3 * face]].x == INT_MIN || svb[faces[3 * face + 1]].x == INT_MIN || svb[faces[3 * face + 2]].x == INT_MIN;
+    }
+  }
+  if (!any_hard) return;
+  int acc[3] = {0, 0, 0};
+  unsigned last_face = 0xffffffffu;
+  int col[3] = {0, 0, 0};
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const unsigned long long k = kv[s];
+    if (k != ~0ull) {
+      const unsigned face = unsigned(k & 0xffffffffu);
+      if (face != last_face) {
+        shade<MODE, true>(svb, faces, sf, &cam, b, res, face, px, py, col);
+        last_face = face;
+      }
+      acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2];
+    }
+  }
+  if (S == 4) { acc[0] = (acc[0] + 2) >> 2; acc[1] = (acc[1] + 2) >> 2; acc[2] = (acc[2] + 2) >> 2; }
+  uint8_t* o = rgb + (size_t(b) * npix + p) * 3;
+  o[0] = uint8_t(acc[0]); o[1] = uint8_t(acc[1]); o[2] = uint8_t(acc[2]);
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int S>
@@ -729,7 +779,7 @@ int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* key
   if (a.primitive == 1) {
     point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res, znear, zfar);
     FP_CUDA(cudaGetLastError());
-    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
+    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
   } else {
     triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res,
                                                                          a.cull_backfaces, znear, zfar);
@@ -737,10 +787,13 @@ int launch_raster(const RasterArgs& a, ScreenVertex* sv, unsigned long long* key
     hard_triangle_kernel<S><<<dim3((a.F + 255) / 256, a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F,
                                                                               a.res, a.cull_backfaces);
     FP_CUDA(cudaGetLastError());
-    if (a.texture != nullptr)
-      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
-    else
-      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, a.rgb, a.depth, a.V, a.res);
+    if (a.texture != nullptr) {
+      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+      resolve_hard_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    } else {
+      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res);
+      resolve_hard_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    }
   }
   FP_CUDA(cudaGetLastError());
   return 0;
@@ -779,7 +832,7 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
       reinterpret_cast<uint8_t*>(workspace) + align_up(size_t(a.B) * a.V * sizeof(ScreenVertex), 256));
   const size_t nkeys = size_t(a.B) * a.res * a.res * a.msaa;
   int* view_hard = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(keys) + align_up(nkeys * 8, 256));
-  ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, a.primitive == 1 ? 4 : 5, stream);  // algorithmic bytes: RGB u8 + depth f32 out
+  ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, a.primitive == 1 ? 4 : 6, stream);  // algorithmic bytes: RGB u8 + depth f32 out
   clear_keys_kernel<<<sm_count() * 8, 256, 0, stream>>>(keys, nkeys);
   FP_CUDA(cudaGetLastError());
   FP_CUDA(cudaMemsetAsync(view_hard, 0, size_t(a.B) * sizeof(int), stream));

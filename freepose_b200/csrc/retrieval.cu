@@ -67,9 +67,16 @@ scan_kernel(const bf16* __restrict__ db, const bf16* __restrict__ queries, long 
   const int row16 = D / 8;
   for (int i = threadIdx.x; i < Q * row16; i += blockDim.x) s_q[i] = reinterpret_cast<const uint4*>(queries)[i];
   __syncthreads();
-  for (long long m = (long long)blockIdx.x * RT_WARPS + warp; m < M; m += (long long)gridDim.x * RT_WARPS) {
+  // the NEXT row of this warp is in flight while the current one is reduced against the Q queries
+  const long long stride = (long long)gridDim.x * RT_WARPS;
+  long long m = (long long)blockIdx.x * RT_WARPS + warp;
+  uint4 nxt[MAX_CHUNKS];
+  if (m < M) load_row(db + m * D, lane, chunks, nxt);
+  for (; m < M; m += stride) {
     uint4 u[MAX_CHUNKS];
-    load_row(db + m * D, lane, chunks, u);
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) u[c] = nxt[c];
+    if (m + stride < M) load_row(db + (m + stride) * D, lane, chunks, nxt);
     for (int q = 0; q < Q; ++q) {
       uint4 qv[MAX_CHUNKS];
 #pragma unroll

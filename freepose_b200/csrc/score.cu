@@ -20,7 +20,7 @@ namespace fp {
 
 namespace {
 
-constexpr int SC_WARPS = 8;
+constexpr int SC_WARPS = 16;   // 512 threads per hypothesis: two rows per warp in flight = 64 KB per CTA
 using namespace rowops;
 
 // qn = normalised (or verbatim) query tokens, one warp per row
@@ -62,10 +62,21 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
   const int b = blockIdx.x;
   const int chunks = D / 256;
   const bf16* base = feats_t + size_t(b) * P * D;
+  // HBM-bound: keep the NEXT row of this warp in flight while the current one is reduced (one row per warp in flight left
+  // the kernel at 1.6 TB/s: load -> dependent reduction -> load)
+  uint4 tn_[MAX_CHUNKS], qn_[MAX_CHUNKS];
+  if (warp < P) {
+    load_row(base + size_t(warp) * D, lane, chunks, tn_);
+    load_row(qn + size_t(warp) * D, lane, chunks, qn_);
+  }
   for (int n = warp; n < P; n += SC_WARPS) {
     uint4 t[MAX_CHUNKS], q[MAX_CHUNKS];
-    load_row(base + size_t(n) * D, lane, chunks, t);
-    load_row(qn + size_t(n) * D, lane, chunks, q);
+#pragma unroll
+    for (int c = 0; c < MAX_CHUNKS; ++c) { t[c] = tn_[c]; q[c] = qn_[c]; }
+    if (n + SC_WARPS < P) {
+      load_row(base + size_t(n + SC_WARPS) * D, lane, chunks, tn_);
+      load_row(qn + size_t(n + SC_WARPS) * D, lane, chunks, qn_);
+    }
     const float nrm = row_norm(t, chunks);
     float acc = 0.f;
 #pragma unroll
