@@ -73,7 +73,7 @@ SIGNATURES = {
     "fp_retrieval_fine": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "fp_softvote_add": (_i, [_vp, _vp, _vp, _i, _i, C.c_int64, _vp]),
     "fp_softvote_mean": (_i, [_vp, _vp, C.c_int64, _i, _vp]),
-    "fp_raster_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "fp_raster_workspace_bytes": (_i, [_i, _i, _i, _i, _i, C.POINTER(_sz)]),
     "fp_rasterize": (_i, [C.POINTER(RasterArgs), _vp, _sz, _vp]),
     "fp_mask_bbox": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fp_crop_resize_pad": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -105,7 +105,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.fp_abi_version() != 2:
+    if lib.fp_abi_version() != 3:
         raise RuntimeError("libfreepose_b200.so ABI version mismatch")
     _lib = lib
     return lib

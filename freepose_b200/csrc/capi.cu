@@ -119,8 +119,8 @@ FP_API int fp_softvote_mean(const float* acc, float* out, int64_t n, int frames,
   return fp::softvote_mean(acc, out, n, frames, S(stream));
 }
 
-FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes) {
-  return fp::raster_workspace_bytes(B, V, res, msaa, bytes);
+FP_API int fp_raster_workspace_bytes(int B, int V, int F, int res, int msaa, size_t* bytes) {
+  return fp::raster_workspace_bytes(B, V, F, res, msaa, bytes);
 }
 
 FP_API int fp_rasterize(const fp_raster_args* g, void* workspace, size_t workspace_bytes, void* stream) {

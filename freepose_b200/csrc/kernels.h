@@ -118,7 +118,7 @@ struct RasterArgs {
   float znear, zfar;      // 0 = 0.05 / 100
   const float* view_k;    // [B, 4] per-view fx, fy, cx, cy or null
 };
-int raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes);
+int raster_workspace_bytes(int B, int V, int F, int res, int msaa, size_t* bytes);
 int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------- geometry

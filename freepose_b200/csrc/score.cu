@@ -78,6 +78,7 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
       load_row(qn + size_t(n + SC_WARPS) * D, lane, chunks, qn_);
     }
     const float nrm = row_norm(t, chunks);
+    const float rnrm = __frcp_rn(nrm);
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < MAX_CHUNKS; ++c)
@@ -87,7 +88,12 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
         unpack8(q[c], qf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float tn = bf16_round(__fdiv_rn(tf[j], nrm));
+          // tn = bf16(t / nrm), the reference's rounding, without an IEEE division per element: q = t * (1/nrm) is
+          // within 2 fp32 ulps of the correctly rounded quotient, so unless q sits within 64 ulps of a bf16 rounding
+          // midpoint (0.4 % of the values) both round to the same bf16; the rest take the exact division.
+          const float qd = __fmul_rn(tf[j], rnrm);
+          const int low = int(__float_as_uint(qd) & 0xffffu) - 0x8000;
+          const float tn = (low > 64 || low < -64) ? bf16_round(qd) : bf16_round(__fdiv_rn(tf[j], nrm));
           acc = __fadd_rn(acc, __fmul_rn(tn, qf[j]));
         }
       }

@@ -229,7 +229,7 @@ def rasterize(verts: torch.Tensor, faces: torch.Tensor, colors, poses: torch.Ten
     assert colors is None or colors.dtype == torch.uint8
     lib = load()
     nbytes = C.c_size_t(0)
-    check(lib.fp_raster_workspace_bytes(B, V, res, msaa, C.byref(nbytes)), "fp_raster_workspace_bytes")
+    check(lib.fp_raster_workspace_bytes(B, V, 0 if points else F, res, msaa, C.byref(nbytes)), "fp_raster_workspace_bytes")
     ws = _ws(nbytes.value, dev)
     rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
     depth = torch.empty(B, res, res, dtype=torch.float32, device=dev)

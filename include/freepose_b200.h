@@ -30,7 +30,7 @@ extern "C" {
 #define FP_API
 #endif
 
-#define FP_ABI_VERSION 2
+#define FP_ABI_VERSION 3
 
 FP_API int fp_abi_version(void);
 FP_API const char* fp_last_error(void);
@@ -191,7 +191,7 @@ typedef struct fp_raster_args {
   float znear, zfar;        /* 0 = pyrender's IntrinsicsCamera defaults 0.05 / 100                           */
   const float* view_k;      /* [B,4] fp32 per-view fx,fy,cx,cy (overrides the four scalars) or NULL          */
 } fp_raster_args;
-FP_API int fp_raster_workspace_bytes(int B, int V, int res, int msaa, size_t* bytes /* host out */);
+FP_API int fp_raster_workspace_bytes(int B, int V, int F, int res, int msaa, size_t* bytes /* host out */);
 FP_API int fp_rasterize(const fp_raster_args* args /* host struct */, void* workspace, size_t workspace_bytes,
                         void* stream);
 

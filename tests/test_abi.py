@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
-    assert lib.fp_abi_version() == 2
+    assert lib.fp_abi_version() == 3
     # no torch / C++ types leak through the boundary: only the declared C symbols are default-visible
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
@@ -54,8 +54,8 @@ def test_argument_errors_are_reported_not_thrown(lib):
     rc = lib.fp_ffa_pool(None, None, 1, 225, 1024, None, None, None)
     assert rc == -1 and b"multiple of 14" in lib.fp_last_error()
     n = ctypes.c_size_t(0)
-    assert lib.fp_raster_workspace_bytes(2, 10, 224, 3, ctypes.byref(n)) == -1
+    assert lib.fp_raster_workspace_bytes(2, 10, 16, 224, 3, ctypes.byref(n)) == -1
     assert b"msaa" in lib.fp_last_error()
-    assert lib.fp_raster_workspace_bytes(2, 10, 224, 4, ctypes.byref(n)) == 0 and n.value > 2 * 224 * 224 * 4 * 8
+    assert lib.fp_raster_workspace_bytes(2, 10, 16, 224, 4, ctypes.byref(n)) == 0 and n.value > 2 * 224 * 224 * 4 * 8
     assert lib.fp_vit_workspace_bytes(1024, 4096, 1, 224) > 261 * (1024 * 2 * 2 + 3072 * 2 + 4096 * 2)
     assert lib.fp_vit_workspace_bytes(768, 3072, 1, 518) > 1374 * (768 * 2 * 2 + 2304 * 2 + 3072 * 2)
