@@ -27,19 +27,23 @@
 // iff all b_i >= 0 and sum > 0; depth |det| / sum; the per-sample test znear < z < zfar then removes exactly what GL's
 // clipping against the near / far planes removes.  Only views that contain such a vertex run that kernel at all.
 //
-// Two pipelines behind one entry point, chosen PER VIEW by a flag the vertex kernel sets:
-//   * TILE pipeline (every view whose vertices all project: the template / hypothesis renders of the hot path).  Triangles
+// Two pipelines behind one entry point.  The GENERAL pipeline is the default for every view; with FP_RASTER_TILE=1 the
+// views whose vertices all project (a flag the vertex kernel sets per view) take the TILE pipeline instead -- an
+// experiment that cut the DRAM traffic as intended but lost on time (see launch_raster):
+//   * TILE pipeline.  Triangles
 //     are binned into 16 x 16-pixel tiles (count -> scan -> fill; triangles spanning more than 2 x 2 tiles go to a per-view
 //     list instead), then ONE kernel per tile depth-tests the samples in SHARED memory, shades and writes RGB + depth.  No
 //     sample-key buffer exists in HBM: the previous pipeline cleared, atomically updated and re-read 32 bytes per pixel
 //     (835 MB per 521 views, 12.6 x the 183 MB of output).
-//   * GENERAL pipeline (views with a vertex behind the near plane / outside the guard band, and point clouds): 64-bit
-//     sample keys in HBM, atomicMin from the triangle / hard-triangle / point kernels, resolve passes.
+//   * GENERAL pipeline (also the only one for views with a vertex behind the near plane / outside the guard band, and
+//     for point clouds): 64-bit sample keys in HBM, atomicMin from the triangle / hard-triangle / point kernels, resolve passes.
 // Both evaluate the same integer edge functions and the same depth expression and keep the minimum (depth, face) key
 // per sample, so they produce identical images.
 //
 // General pipeline kernels: clear keys -> vertex transform -> triangle (32-bit edge functions for small triangles, warp-cooperative walk
 // for large ones) or point scatter -> resolve (one thread per pixel; coalesced depth, shuffle-assembled RGB words).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -679,7 +683,10 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
   const int b = blockIdx.y;
   if (route != nullptr && !route[b]) return;
   const int npix = res * res;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // (the grid may be smaller than the image: a routed launch keeps it small so that the CTAs of views that are not
+  // its business cost nothing to retire)
+  for (int blk = blockIdx.x; blk * int(blockDim.x) < npix; blk += gridDim.x) {
+  const int p = blk * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp_base = p - lane;
   if (warp_base >= npix) return;
@@ -732,6 +739,7 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
   } else if (live) {
     out[3 * lane] = uint8_t(acc[0]); out[3 * lane + 1] = uint8_t(acc[1]); out[3 * lane + 2] = uint8_t(acc[2]);
   }
+  }
 }
 
 // Second resolve pass for the views flagged by the vertex kernel: pixels with at least one sample won by a hard triangle
@@ -745,8 +753,7 @@ resolve_hard_kernel(const unsigned long long* __restrict__ keys, const ScreenVer
   const int b = blockIdx.y;
   if (!view_hard[b]) return;
   const int npix = res * res;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npix) return;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
   const int py = p / res, px = p - py * res;
   const ScreenVertex* svb = sv + size_t(b) * V;
   const unsigned long long* kv = keys + (size_t(b) * npix + p) * S;
@@ -759,7 +766,7 @@ resolve_hard_kernel(const unsigned long long* __restrict__ keys, const ScreenVer
       any_hard |= svb[faces[3 * face]].x == INT_MIN || svb[faces[3 * face + 1]].x == INT_MIN || svb[faces[3 * face + 2]].x == INT_MIN;
     }
   }
-  if (!any_hard) return;
+  if (!any_hard) continue;
   int acc[3] = {0, 0, 0};
   unsigned last_face = 0xffffffffu;
   int col[3] = {0, 0, 0};
@@ -778,6 +785,7 @@ resolve_hard_kernel(const unsigned long long* __restrict__ keys, const ScreenVer
   if (S == 4) { acc[0] = (acc[0] + 2) >> 2; acc[1] = (acc[1] + 2) >> 2; acc[2] = (acc[2] + 2) >> 2; }
   uint8_t* o = rgb + (size_t(b) * npix + p) * 3;
   o[0] = uint8_t(acc[0]); o[1] = uint8_t(acc[1]); o[2] = uint8_t(acc[2]);
+  }
 }
 
 // ================================================================================================================
@@ -928,8 +936,8 @@ __device__ __forceinline__ void fill_rule_bias(const TriSetup& t, long long (&bi
 
 // One CTA per (tile, view): depth test in shared memory, then shade + write.  Outputs of tiles without triangles were
 // zeroed by a memset.  MODE 0 = vertex colours, 1 = texture.
-template <int S, int MODE>
-__global__ void __launch_bounds__(256)
+template <int S, int MODE, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 tile_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ faces, const Surface sf,
             const int* __restrict__ route, const int* __restrict__ tile_offset, const int* __restrict__ bin_list,
             const int* __restrict__ big_count, const int4* __restrict__ big_list, uint8_t* __restrict__ rgb,
@@ -1062,6 +1070,30 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
     return 0;
   }
   const dim3 fgrid((a.F + 255) / 256, a.B);
+  // FP_RASTER_TILE=1 selects the tile pipeline for the views it can take.  It is NOT the default: measured at the benchmark
+  // shape (521 views x 20 480 faces, 224^2, ~1.3 px per triangle) it moves 4 x less DRAM but takes 3.7 ms against 2.2 ms --
+  // both pipelines are bound by the per-triangle instruction stream (set-up in 64-bit integers, IEEE divisions in the depth
+  // interpolation), which the tile pipeline runs three times (two binning passes + the tile kernel) instead of once, and
+  // whose latency its 2-4 resident CTAs per SM hide less well than the 24 warps of triangle_kernel (profiles/r02e_*).
+  static const int use_tile = [] { const char* e = getenv("FP_RASTER_TILE"); return e ? atoi(e) : 0; }();
+  if (!use_tile) {
+    clear_keys_kernel<<<cgrid, 256, 0, stream>>>(keys, per_view, nullptr);
+    FP_CUDA(cudaGetLastError());
+    triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, nullptr);
+    FP_CUDA(cudaGetLastError());
+    hard_triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
+    FP_CUDA(cudaGetLastError());
+    const dim3 hgrid(min((a.res * a.res + 255) / 256, 24), a.B);
+    if (a.texture != nullptr) {
+      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr);
+      resolve_hard_kernel<S, 1><<<hgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    } else {
+      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr);
+      resolve_hard_kernel<S, 0><<<hgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    }
+    FP_CUDA(cudaGetLastError());
+    return 0;
+  }
   // ---- tile pipeline (views with route == 0)
   int* tile_count = reinterpret_cast<int*>(ws + w.counters);
   const size_t ntiles = size_t(a.B) * w.ntx * w.nty;
@@ -1083,26 +1115,32 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
                                            tile_offset, bin_list, big_count, big_list);
   FP_CUDA(cudaGetLastError());
   const dim3 tgrid(w.ntx * w.nty, a.B);
-  if (a.texture != nullptr)
-    tile_kernel<S, 1><<<tgrid, 256, 0, stream>>>(sv, a.faces, sf, view_hard, tile_offset, bin_list, big_count, big_list, a.rgb,
-                                                 a.depth, a.V, a.F, a.res, w.ntx, w.nty, a.cull_backfaces, znear, zfar);
-  else
-    tile_kernel<S, 0><<<tgrid, 256, 0, stream>>>(sv, a.faces, sf, view_hard, tile_offset, bin_list, big_count, big_list, a.rgb,
-                                                 a.depth, a.V, a.F, a.res, w.ntx, w.nty, a.cull_backfaces, znear, zfar);
+  static const int occ = [] { const char* e = getenv("FP_TILE_OCC"); return e ? atoi(e) : 4; }();   // perf experiments
+#define FP_TILE_LAUNCH(MODE_, OCC_)                                                                                              \
+  tile_kernel<S, MODE_, OCC_><<<tgrid, 256, 0, stream>>>(sv, a.faces, sf, view_hard, tile_offset, bin_list, big_count, big_list, \
+                                                         a.rgb, a.depth, a.V, a.F, a.res, w.ntx, w.nty, a.cull_backfaces, znear, zfar)
+  if (a.texture != nullptr) {
+    if (occ == 2) FP_TILE_LAUNCH(1, 2); else if (occ == 3) FP_TILE_LAUNCH(1, 3); else FP_TILE_LAUNCH(1, 4);
+  } else {
+    if (occ == 2) FP_TILE_LAUNCH(0, 2); else if (occ == 3) FP_TILE_LAUNCH(0, 3); else FP_TILE_LAUNCH(0, 4);
+  }
+#undef FP_TILE_LAUNCH
   FP_CUDA(cudaGetLastError());
-  // ---- general pipeline (views with route == 1: every kernel returns at once for the others)
-  clear_keys_kernel<<<cgrid, 256, 0, stream>>>(keys, per_view, view_hard);
+  // ---- general pipeline (views with route == 1: every kernel returns at once for the others; small grids, the kernels
+  //      loop, so that those returns cost next to nothing)
+  const dim3 rgrid_routed(min((a.res * a.res + 255) / 256, 24), a.B);
+  clear_keys_kernel<<<dim3(min(cgrid.x, 8u), a.B), 256, 0, stream>>>(keys, per_view, view_hard);
   FP_CUDA(cudaGetLastError());
   triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, view_hard);
   FP_CUDA(cudaGetLastError());
   hard_triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
   FP_CUDA(cudaGetLastError());
   if (a.texture != nullptr) {
-    resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
-    resolve_hard_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    resolve_kernel<S, 1><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
+    resolve_hard_kernel<S, 1><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
   } else {
-    resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
-    resolve_hard_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
+    resolve_kernel<S, 0><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
+    resolve_hard_kernel<S, 0><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
   }
   FP_CUDA(cudaGetLastError());
   return 0;
