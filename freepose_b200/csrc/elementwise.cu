@@ -17,12 +17,11 @@ template <int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
                  bf16* __restrict__ out, int rows, float eps, int in_group_stride, int in_skip,
-                 int rows_per_group, int reverse) {
+                 int rows_per_group) {
   constexpr int LN_D = NCH * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * LN_WARPS + warp;
-  if (r0 >= rows) return;
-  const int r = reverse ? rows - 1 - r0 : r0;   // (CTAs are dispatched in index order: reversed = last rows first)
+  const int r = blockIdx.x * LN_WARPS + warp;
+  if (r >= rows) return;
   const int grp = r / rows_per_group;
   const int idx = r - grp * rows_per_group;
   const size_t in_row = size_t(grp) * in_group_stride + in_skip + idx;
@@ -130,7 +129,7 @@ special_tokens_kernel(const bf16* __restrict__ special, bf16* __restrict__ token
 }  // namespace
 
 int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int rows, int D, float eps,
-                   int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream, int reverse) {
+                   int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream) {
   FP_REQUIRE(D == 1024 || D == 768, "layernorm: D=%d unsupported (ViT-L: 1024, ViT-B: 768)", D);
   if (rows <= 0) return 0;
   FP_REQUIRE(rows_per_group > 0, "layernorm: rows_per_group must be positive");
@@ -138,10 +137,10 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int r
   ProfScope prof(PROF_LAYERNORM, 2.0 * double(rows) * D * 2, 1, stream);
   if (D == 1024)
     layernorm_kernel<4><<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
-                                                              rows_per_group, reverse);
+                                                              rows_per_group);
   else
     layernorm_kernel<3><<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
-                                                              rows_per_group, reverse);
+                                                              rows_per_group);
   FP_CUDA(cudaGetLastError());
   return 0;
 }

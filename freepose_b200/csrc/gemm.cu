@@ -51,7 +51,6 @@ struct Params {
   int tokens_per_img;
   int token_offset;
   int debug;  // perf experiments only: 1 = skip epilogue stores, 2 = always load tile (0,0)
-  int reverse;  // walk the M blocks from the last to the first (see GemmArgs::reverse)
 };
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per issue slot) -------------------
@@ -310,8 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_lin = tile / num_n_tiles, n_blk = tile % num_n_tiles;
-        const int m_blk = p.reverse ? num_m_tiles - 1 - m_lin : m_lin;
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
@@ -361,8 +359,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_lin = tile / num_n_tiles, n_blk = tile % num_n_tiles;
-        const int m_blk = p.reverse ? num_m_tiles - 1 - m_lin : m_lin;
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM + q * 32 + lane;
       EpiPrefetch pf;
       epilogue_prefetch<MODE>(p, epi_stage, grp, lane, row, n_blk, pf);
@@ -446,8 +443,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_lin = tile / num_n_tiles, n_blk = tile % num_n_tiles;
-        const int m_blk = p.reverse ? num_m_tiles - 1 - m_lin : m_lin;
+        const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // both CTAs' bytes
@@ -499,8 +495,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_lin = tile / num_n_tiles, n_blk = tile % num_n_tiles;
-        const int m_blk = p.reverse ? num_m_tiles - 1 - m_lin : m_lin;
+      const int m_blk = tile / num_n_tiles, n_blk = tile % num_n_tiles;
       const int row = m_blk * BM2 + int(rank) * BM + q * 32 + lane;
       EpiPrefetch pf;
       epilogue_prefetch<MODE>(p, epi_stage, grp, lane, row, n_blk, pf);
@@ -580,7 +575,6 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.token_offset = a.token_offset;
   static const int dbg = [] { const char* e = getenv("FP_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
-  p.reverse = a.reverse;
   switch (a.mode) {
     case EPI_BIAS: return two ? launch2<EPI_BIAS>(tmA, tmB, tmOut, p, stream) : launch<EPI_BIAS>(tmA, tmB, tmOut, p, stream);
     case EPI_BIAS_GELU:

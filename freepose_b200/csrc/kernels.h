@@ -31,10 +31,6 @@ struct GemmArgs {
   const bf16* gamma;  // [N]             (EPI_BIAS_LS_RES)
   const bf16* res;    // [M, ldo] residual (EPI_BIAS_LS_RES, may alias out) | pos-embed [1+P, N] (EPI_PATCH_EMBED)
   int patches_per_img, tokens_per_img, token_offset;  // EPI_PATCH_EMBED row remap
-  // Row-block order.  Consecutive kernels of a ViT block walk the rows in OPPOSITE directions (vit.cu): a kernel then
-  // starts with the rows its producer wrote last, which are still in the 126 MB L2 (the activations of a 521-image
-  // step are 278 MB .. 1.1 GB per tensor, so walking them in the same direction always misses).
-  int reverse;
 };
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 
@@ -57,7 +53,7 @@ int attention_split_bf16(const bf16* qkv, bf16* out, int B, int T, int H, float 
 // after skipping `in_skip` leading rows of every `in_group_stride`-row input group (used by the
 // final norm to drop cls + register tokens while normalising).
 int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int rows, int D, float eps,
-                   int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream, int reverse = 0);
+                   int in_group_stride, int in_skip, int rows_per_group, cudaStream_t stream);
 
 // Image (B, 3, res, res) -> patch matrix [B*g*g, Kpad] (col = c*196 + ky*14 + kx, zero padded).
 // src_is_f32 = 1: fp32 [0,1] image, the reference's bf16 Normalize is applied on the fly;

@@ -1,8 +1,6 @@
 // DINOv2 ViT-L/14-reg (or ViT-B/14-reg: dim 768, 12 heads, MLP 3072) forward to layer L + final norm (reference src/pipeline/retrieval/dino.py:14-32):
 // sequencing of the kernels over caller-provided workspace.  Stateless: weights and buffers are borrowed
 // device pointers (include/freepose_b200.h: fp_vit_weights / fp_vit_forward).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "kernels.h"
 #include "freepose_b200.h"
@@ -70,16 +68,12 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
     if (int rc = gemm_bf16(a, stream)) return rc;
   }
 
-  // ---- transformer blocks.  Row order (GemmArgs::reverse): proj / fc2 write the residual stream in one direction and
-  // the LayerNorm behind them reads it in the other, and so on down the chain, so that every kernel starts on the rows
-  // its producer has just written (still in L2):  LN1 <-  qkv ->  attention ->  proj <-  LN2 ->  fc1 <-  fc2 ->
-  // FP_VIT_ALTERNATE=0 walks everything forwards (A/B measurements).
-  static const int alternate = [] { const char* e = getenv("FP_VIT_ALTERNATE"); return e ? atoi(e) : 1; }();
+  // ---- transformer blocks
   const float scale = 0.125f;  // head_dim^-0.5
   for (int l = 0; l < layer; ++l) {
     const fp_vit_layer& L = w->layers[l];
     auto P16 = [](const void* p) { return reinterpret_cast<const bf16*>(p); };
-    if (int rc = layernorm_bf16(x, P16(L.ln1_w), P16(L.ln1_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream, alternate)) return rc;
+    if (int rc = layernorm_bf16(x, P16(L.ln1_w), P16(L.ln1_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
     GemmArgs a{};
     a.A = h; a.lda = D; a.W = P16(L.qkv_w); a.out = qkv; a.ldo = 3 * D; a.M = int(M); a.N = 3 * D; a.K = D;
     a.mode = EPI_BIAS; a.bias = P16(L.qkv_b);
@@ -87,12 +81,12 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
     if (int rc = attention_bf16(qkv, h, B, T, HEADS, scale, stream)) return rc;
     a = GemmArgs{};
     a.A = h; a.lda = D; a.W = P16(L.proj_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = D;
-    a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.proj_b); a.gamma = P16(L.ls1); a.res = x; a.reverse = alternate;
+    a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.proj_b); a.gamma = P16(L.ls1); a.res = x;
     if (int rc = gemm_bf16(a, stream)) return rc;
-    if (int rc = layernorm_bf16(x, P16(L.ln2_w), P16(L.ln2_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream, 0)) return rc;
+    if (int rc = layernorm_bf16(x, P16(L.ln2_w), P16(L.ln2_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
     a = GemmArgs{};
     a.A = h; a.lda = D; a.W = P16(L.fc1_w); a.out = mlp; a.ldo = MLP; a.M = int(M); a.N = MLP; a.K = D;
-    a.mode = EPI_BIAS_GELU; a.bias = P16(L.fc1_b); a.reverse = alternate;
+    a.mode = EPI_BIAS_GELU; a.bias = P16(L.fc1_b);
     if (int rc = gemm_bf16(a, stream)) return rc;
     a = GemmArgs{};
     a.A = mlp; a.lda = MLP; a.W = P16(L.fc2_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = MLP;
