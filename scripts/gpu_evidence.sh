@@ -5,7 +5,11 @@ set -u
 O=gpurun_out
 mkdir -p $O
 T="${1:-r02f}"
-timeout 700 python -m pytest tests -m gpu -x -q > $O/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -2 $O/${T}_tests.log
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  timeout 700 python -m pytest tests -m gpu -x -q > $O/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -2 $O/${T}_tests.log
+fi
+# (.ncu-rep files are summarised on the box and deleted: gpurun only brings back 64 MiB)
+summ() { python profiles/summarize.py full $O/$1.ncu-rep $O/$1_full.txt && rm -f $O/$1.ncu-rep; }
 timeout 300 python bench.py --steps 20 --warmup 3 > $O/${T}_bench.json 2> $O/${T}_bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --res 420 --hyp 600 --chunk 150 --no-cpu-baseline > $O/${T}_bench_420.json 2>/dev/null; echo "bench420 rc=$?"
 timeout 300 python bench.py --config ffa --steps 196 --warmup 3 > $O/${T}_ffa.json 2>/dev/null; echo "ffa rc=$?"
@@ -13,11 +17,13 @@ timeout 300 python bench.py --config video --steps 300 --warmup 3 > $O/${T}_vide
 timeout 300 python bench.py --config refiner --steps 20 --warmup 3 > $O/${T}_refiner.json 2>/dev/null; echo "refiner rc=$?"
 # ncu: launch list of one full-depth step (shares), then full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches.csv python profiles/prof_step.py 2 520 22 > /dev/null 2>&1; echo "launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -o $O/${T}_step2layers -f python profiles/prof_step.py 1 520 2 > $O/${T}_ncu_step.log 2>&1; echo "ncu step rc=$?"
-ATTN_B=150 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_pair -s 2 -c 1 -o $O/${T}_attention_pair -f python tests/dev_attn_bench.py 905 > $O/${T}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:scan_kernel|topk_large|fine_kernel" -c 3 -o $O/${T}_retrieval -f python tests/dev_retrieval_bench.py > $O/${T}_ncu_retr.log 2>&1; echo "ncu retrieval rc=$?"
-FP_RASTER_TILE=1 timeout 300 ncu --set full --clock-control none -k "regex:tile_kernel|bin_kernel|tile_scan" -s 4 -c 4 -o $O/${T}_raster_tile -f python tests/dev_raster_once.py > $O/${T}_ncu_tile.log 2>&1; echo "ncu tile rc=$?"
+timeout 900 ncu --set full --clock-control none -o $O/${T}_step1layer -f python profiles/prof_step.py 1 520 1 > $O/${T}_ncu_step.log 2>&1; echo "ncu step rc=$?"; summ ${T}_step1layer
+ATTN_B=150 timeout 300 ncu --set full --clock-control none -k regex:attention_pair -s 2 -c 1 -o $O/${T}_attention_pair -f python tests/dev_attn_bench.py 905 > $O/${T}_ncu_pair.log 2>&1; echo "ncu pair rc=$?"; summ ${T}_attention_pair
+timeout 300 ncu --set full --clock-control none -k "regex:scan_kernel|topk_large|fine_kernel" -c 3 -o $O/${T}_retrieval -f python tests/dev_retrieval_bench.py > $O/${T}_ncu_retr.log 2>&1; echo "ncu retrieval rc=$?"; summ ${T}_retrieval
+FP_RASTER_TILE=1 timeout 300 ncu --set full --clock-control none -k "regex:tile_kernel|bin_kernel|tile_scan" -s 4 -c 4 -o $O/${T}_raster_tile -f python tests/dev_raster_once.py > $O/${T}_ncu_tile.log 2>&1; echo "ncu tile rc=$?"; summ ${T}_raster_tile
 # compute-sanitizer memcheck on a narrowed selection (one GEMM set, the two new attention kernels, raster incl. clipping)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_kernels.py -x -q \
   -k "test_gemm_epilogues or (test_attention and 2-261) or (tiled_keys and 1-273) or (raster_bit_exact and 3-224-4-False) or near_plane" \
   > $O/${T}_sanitizer.log 2>&1; echo "sanitizer rc=$?"; tail -4 $O/${T}_sanitizer.log
+python profiles/summarize.py launches $O/${T}_launches.csv $O/${T}_launches_summary.txt; rm -f $O/${T}_launches.csv
+rm -f $O/*.ncu-rep; du -sh $O
