@@ -32,6 +32,7 @@ class DinoOnlinePoseEstimator(nn.Module):
         self.rendering_scale = 0.25
         self.device = self.coarse_estimator.device
         self._scaled_meshes = {}   # id(mesh) -> (mesh, mesh at rendering scale): uploaded / mip-mapped once, not per frame
+        self._fine_rot = None      # (n_fine, 9) rotation parts, for the neighbourhood pre-filter
 
     def to(self, *args, **kwargs):
         return self
@@ -41,6 +42,21 @@ class DinoOnlinePoseEstimator(nn.Module):
         diffs = render_poses[:, :3, :3] @ query_pose[:3, :3].T
         d = _rotvec_angle(diffs)
         return np.rad2deg(d) if degrees else d
+
+    def neighbourhood(self, prev_pose, neighborhood=15):
+        """Indices of the fine poses within `neighborhood` degrees of prev_pose -- np.where(geodesic_distance(...) <
+        neighborhood) of online_pose_estimator.py:55-56.  The 20 000 candidates are pre-filtered by the trace of
+        R_i R_prev^T (cos of the angle: 9 multiply-adds per pose) with a one-degree margin; the exact rotation-vector
+        angle is evaluated only on the ~25 survivors, so the selected set is the reference's."""
+        Rq = prev_pose[:3, :3]
+        if self._fine_rot is None:
+            self._fine_rot = np.ascontiguousarray(self.fine_mesh_poses[:, :3, :3].reshape(-1, 9))
+        tr = self._fine_rot @ Rq.reshape(9)
+        cand = np.nonzero(tr > 1.0 + 2.0 * np.cos(np.deg2rad(min(neighborhood + 1.0, 180.0))))[0]
+        if neighborhood + 1.0 >= 180.0:
+            cand = np.arange(len(self.fine_mesh_poses))
+        d = self.geodesic_distance(self.fine_mesh_poses[cand], prev_pose)
+        return cand[d < neighborhood]
 
     def forward(self, proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose=None,
                 neighborhood=15, layer=22, batch_size=128, mask_scores=False):
@@ -72,18 +88,26 @@ class DinoOnlinePoseEstimator(nn.Module):
     def forward_fine(self, proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose,
                      neighborhood=15, layer=22, mask_scores=False, query_feat=None):
         normalise_query = query_feat is None
-        if query_feat is None:
-            query_feat = self.feature_extractor(proposal[None], layer=layer, feature_type="patch")
-        dists = self.geodesic_distance(self.fine_mesh_poses, np.asarray(prev_pose))
-        close = np.where(dists < neighborhood)[0]
+        close = self.neighbourhood(np.asarray(prev_pose), neighborhood)
         if close.size == 0:
             raise ValueError("no fine pose within the neighbourhood of prev_pose")
         selected = self.fine_mesh_poses[close]
         m = self._scaled_mesh(mesh)
         rgb, depth = self.renderer.render_device(m, selected)
         T = self.renderer.resolution
-        patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
-        feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+        B, P = len(close), (T // 14) ** 2
+        if query_feat is None:
+            # frames > 0: the query crop rides in the same batch as the ~19 fine renders (one ViT forward instead of two;
+            # the reference runs it as a separate batch of one, online_pose_estimator.py:50-52 -- same arithmetic per image)
+            patches = torch.empty((B + 1) * P, ops.KPAD, dtype=torch.bfloat16, device=self.device)
+            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches)
+            q = torch.as_tensor(proposal).to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            ops.im2col(q[None], out=patches[B * P:])
+            both = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+            feats, query_feat = both[:B], both[B:]
+        else:
+            patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
+            feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
         weights = None
         if mask_scores:
             g = T // 14

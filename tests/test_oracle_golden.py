@@ -312,9 +312,15 @@ def test_fine_stage_neighbourhood_matches_reference(golden):
     g = golden["online_fine"]
     fine = np.array(generate_poses(20000))
     assert hashlib.sha256(np.ascontiguousarray(fine).tobytes()).hexdigest() == str(g["fine_sha"])
+    class Sel:                                   # the estimator's selection method without constructing the CUDA engine
+        fine_mesh_poses, _fine_rot = fine, None
+        geodesic_distance = staticmethod(DinoOnlinePoseEstimator.geodesic_distance)
+        neighbourhood = DinoOnlinePoseEstimator.neighbourhood
+    sel = Sel()
     for i, T in enumerate(g["prev_poses"]):
         d = DinoOnlinePoseEstimator.geodesic_distance(fine, T)
         for nb in (15, 5):
             assert np.array_equal(np.where(d < nb)[0], g[f"close_{i}_{nb}"]), (i, nb)
+            assert np.array_equal(sel.neighbourhood(T, nb), g[f"close_{i}_{nb}"]), (i, nb)     # pre-filtered path
         np.testing.assert_allclose(d[g[f"close_{i}_15"]], g[f"dist_{i}"], rtol=0, atol=1e-6)
     assert 1234 in g["close_6_5"] and len(g["close_1_5"]) == 0        # a fine pose finds itself; 5 degrees can be empty
