@@ -549,15 +549,19 @@ def setup_video(args, rank, world, dev):
     def step_e2e():
         props = Proposals(img, {"boxes": torch.from_numpy(boxes), "masks": torch.from_numpy(masks)}, args.res,
                           bbox_extend=0.05)
-        outs = []
-        for j in mine:
-            first = prev[j] is None
-            out = model(props.proposals[j], props.proposals_masks[j], entries[j], meshes_full[j], K,
-                        boxes[j].astype(np.float64), 0.3, prev_pose=prev[j], neighborhood=15, layer=args.layer,
-                        batch_size=128)
+        items = [dict(proposal=props.proposals[j], proposal_mask=props.proposals_masks[j], template_dict=entries[j],
+                      mesh=meshes_full[j], K=K, bbox=boxes[j].astype(np.float64), est_scale=0.3, prev_pose=prev[j])
+                 for j in mine]
+        first = [prev[j] is None for j in mine]
+        if args.per_proposal:                      # the reference's loop: one estimator call per proposal
+            outs = [model(it["proposal"], it["proposal_mask"], it["template_dict"], it["mesh"], it["K"], it["bbox"],
+                          it["est_scale"], prev_pose=it["prev_pose"], neighborhood=15, layer=args.layer, batch_size=128)
+                    for it in items]
+        else:                                      # all proposals of the frame in one ViT pass
+            outs = model.forward_batch(items, neighborhood=15, layer=args.layer, batch_size=128)
+        for j, out, f in zip(mine, outs, first):
             prev[j] = out["TCO"][0]
-            count["hyp"] += len(out["selected_poses"]) + (args.hyp if first else 0)
-            outs.append(out)
+            count["hyp"] += len(out["selected_poses"]) + (args.hyp if f else 0)
         return outs
 
     def reset():
@@ -569,7 +573,8 @@ def setup_video(args, rank, world, dev):
     return dict(metric=f"video frames/sec (8 proposals/frame, coarse->fine, crops @{args.res}^2)", unit="frames/s",
                 units_per_step=1.0 / world, step_device=None, step_e2e=step_e2e, counters=count, reset=reset,
                 h2d=img.size + masks.size + boxes.size * 4, d2h=len(mine) * (8 * 8 + 4 + 4),
-                api="Proposals(frame_host_u8, masks, boxes) + DinoOnlinePoseEstimator.forward(..., prev_pose) per proposal",
+                api="Proposals(frame_host_u8, masks, boxes) + DinoOnlinePoseEstimator." +
+                    ("forward(..., prev_pose) per proposal" if args.per_proposal else "forward_batch(proposals of the frame)"),
                 flops_per_unit=None,
                 workload={"workload": "dino_inference_video (BASELINE configs[3]): 640x480 synthetic frames, 8 proposals per "
                                       f"frame, {args.hyp} coarse hypotheses on the first frame, then the fine poses within 15 "
@@ -694,6 +699,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline and parity legs")
     ap.add_argument("--config", default="pose", choices=["pose", "ffa", "video", "refiner"],
                     help="pose = BASELINE configs[1] (the headline line); ffa / video / refiner = configs[2] / [3] / [4]")
+    ap.add_argument("--per-proposal", action="store_true",
+                    help="video: one estimator call per proposal (the reference's loop) instead of forward_batch per frame")
     ap.add_argument("--batch", type=int, default=None, help="ffa: renders per batch (256); refiner: renders per frame (64)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one proposal per GPU per step; strong: one proposal, hypotheses sharded over the GPUs")

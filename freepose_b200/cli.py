@@ -289,16 +289,19 @@ def run_dino_inference_video(argv=None):
         # a static synthetic scene observed for N frames: exercises the prev_pose carry of the reference loop
         props = Proposals(img0, {"boxes": torch.from_numpy(boxes0), "masks": torch.from_numpy(masks0)},
                           args.resolution, bbox_extend=args.bbox_extend)
-        for j in range(len(boxes0)):
-            prop, pmask = props.proposals[j], props.proposals_masks[j]
-            if args.no_rescore:
-                out = model.coarse_estimator(prop, entries[j], K, boxes0[j].astype(np.float64), 0.3, layer=args.layer,
-                                             batch_size=args.batch_size)
-            else:
-                out = model(prop, pmask, entries[j], meshes_full[j], K, boxes0[j].astype(np.float64), 0.3,
-                            prev_pose=prev_poses[j], neighborhood=args.neighborhood, layer=args.layer,
-                            batch_size=args.batch_size, mask_scores=args.mask_scores)
+        if args.no_rescore:
+            outs = [model.coarse_estimator(props.proposals[j], entries[j], K, boxes0[j].astype(np.float64), 0.3,
+                                           layer=args.layer, batch_size=args.batch_size) for j in range(len(boxes0))]
+        else:
+            # all proposals of the frame in one ViT pass (same results as one model(...) call per proposal)
+            items = [dict(proposal=props.proposals[j], proposal_mask=props.proposals_masks[j], template_dict=entries[j],
+                          mesh=meshes_full[j], K=K, bbox=boxes0[j].astype(np.float64), est_scale=0.3,
+                          prev_pose=prev_poses[j]) for j in range(len(boxes0))]
+            outs = model.forward_batch(items, neighborhood=args.neighborhood, layer=args.layer,
+                                       batch_size=args.batch_size, mask_scores=args.mask_scores)
+            for j, out in enumerate(outs):
                 prev_poses[j] = out["TCO"][0]
+        for j, out in enumerate(outs):
             _csv_row(results, 0, frame, entries[j]["model_name"], out, boxes0[j], 0.3, 1.0, -1)
     out_path = Path(args.out or "./data/results/synthetic/video_pose_outputs.csv")
     _write_csv(results, out_path)

@@ -124,3 +124,74 @@ class DinoOnlinePoseEstimator(nn.Module):
         TCO = tco_from_extents(bbox, dx, dy, K, selected[top_index])
         return {"TCO": [TCO], "scores": [top_val[0].float().cpu().numpy()], "proposal": proposal, "K": K,
                 "bbox": bbox, "all_scores": scores, "selected_poses": selected}
+
+    # ---------------------------------------------------------------- B200-native: all proposals of a frame at once
+    @torch.inference_mode()
+    @on_device
+    def forward_batch(self, items, neighborhood=15, layer=22, batch_size=128, mask_scores=False):
+        """``forward`` for all proposals of a frame in ONE ViT pass.  ``items``: a list of dicts with the keyword
+        arguments of ``forward`` (proposal, proposal_mask, template_dict, mesh, K, bbox, est_scale, prev_pose).  Returns
+        the list of ``forward`` results, identical to calling ``forward`` per proposal (the arithmetic per image does not
+        depend on the batch it rides in).
+
+        Why: the fine stage of one proposal is ~19 renders + 1 query crop = 5 220 token rows -- 84 GEMM tiles on 74 CTA
+        pairs (half the second wave idle) and ~200 launches of ~10 us kernels; the reference's per-proposal loop
+        (scripts/dino_inference_video.py:134-156) leaves a B200 launch- and wave-bound.  With the 8 proposals of a frame in
+        one batch the same kernels run at 41 760 rows."""
+        T = self.renderer.resolution
+        P = (T // 14) ** 2
+        plans = []
+        for it in items:
+            prev_pose, query_feat = it.get("prev_pose"), None
+            if prev_pose is None:          # first frame: coarse stage per proposal (template features are cached per mesh)
+                coarse = self.coarse_estimator.forward(it["proposal"], it["template_dict"], it["K"], it["bbox"],
+                                                       it["est_scale"], layer, batch_size, return_query_feat=True)
+                query_feat, prev_pose = coarse["query_feat"], coarse["TCO"][0]   # raw query: reference quirk kept
+            close = self.neighbourhood(np.asarray(prev_pose), neighborhood)
+            if close.size == 0:
+                raise ValueError("no fine pose within the neighbourhood of prev_pose")
+            plans.append({"it": it, "close": close, "selected": self.fine_mesh_poses[close], "query_feat": query_feat})
+        n_img = sum(len(pl["close"]) + (pl["query_feat"] is None) for pl in plans)
+        patches = torch.empty(n_img * P, ops.KPAD, dtype=torch.bfloat16, device=self.device)
+        row = 0
+        for pl in plans:
+            B = len(pl["close"])
+            rgb, depth = self.renderer.render_device(self._scaled_mesh(pl["it"]["mesh"]), pl["selected"])
+            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches[row * P:])
+            pl.update(depth=depth, masks=masks, lo=row, hi=row + B)
+            row += B
+            if pl["query_feat"] is None:
+                q = torch.as_tensor(pl["it"]["proposal"]).to(self.device, dtype=torch.float32, non_blocking=True)
+                ops.im2col(q.contiguous()[None], out=patches[row * P:(row + 1) * P])
+                pl["q_row"] = row
+                row += 1
+        feats_all = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
+        g = T // 14
+        tops = []
+        for pl in plans:
+            feats = feats_all[pl["lo"]:pl["hi"]]
+            normalise = pl["query_feat"] is None
+            qf = feats_all[pl["q_row"]:pl["q_row"] + 1] if normalise else pl["query_feat"]
+            weights = None
+            if mask_scores:
+                pm = torch.as_tensor(pl["it"]["proposal_mask"]).to(self.device).bool()
+                mk = torch.logical_or(pl["masks"].bool(), pm[None]).float()
+                weights = F.interpolate(mk[None], size=(g, g), mode="bilinear")[0].reshape(len(pl["close"]), g * g).contiguous()
+            scores, top_idx, top_val, _ = ops.score_topk(feats, qf, k=1, weights=weights, normalise_query=normalise)
+            td = pl["it"].get("template_dict")
+            K_t = np.asarray(td["intrinsic"]) if td is not None else \
+                np.array([[self.renderer.focal, 0, T / 2], [0, self.renderer.focal, T / 2], [0, 0, 1]])
+            ext = ops.depth_extents(pl["depth"], K_t, view_idx=top_idx)
+            pl["scores"] = scores
+            tops.append(torch.cat((top_idx.double(), top_val.double(), ext.reshape(-1))))
+        host = torch.stack(tops).cpu().numpy()          # ONE device -> host read for the whole frame
+        outs = []
+        for pl, h in zip(plans, host):
+            it = pl["it"]
+            top_index = int(h[0])
+            dx, dy = rescaled_extents(h[2:10], it["est_scale"], recentre=False)
+            TCO = tco_from_extents(it["bbox"], dx, dy, it["K"], pl["selected"][top_index])
+            outs.append({"TCO": [TCO], "scores": [np.float32(h[1])], "proposal": it["proposal"], "K": it["K"],
+                         "bbox": it["bbox"], "all_scores": pl["scores"], "selected_poses": pl["selected"]})
+        return outs
+

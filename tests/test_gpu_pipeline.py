@@ -250,6 +250,20 @@ def test_online_estimator_coarse_to_fine(lib, sd2):
     out_m = est.forward_fine(query, torch.ones(224, 224, dtype=torch.bool), None, mesh_full, K, bbox, 0.3, qpose,
                              neighborhood=15, layer=2, mask_scores=True)
     assert np.isfinite(out_m["scores"][0])
+    # forward_batch (all proposals of a frame in one ViT pass) == one forward_fine per proposal, bit for bit
+    q2, qpose2 = synthetic_query(mesh_r, 224, seed=5)
+    pm = torch.ones(224, 224, dtype=torch.bool)
+    items = [dict(proposal=query, proposal_mask=pm, template_dict=None, mesh=mesh_full, K=K, bbox=bbox, est_scale=0.3,
+                  prev_pose=qpose),
+             dict(proposal=q2, proposal_mask=pm, template_dict=None, mesh=mesh_full, K=K, bbox=bbox, est_scale=0.25,
+                  prev_pose=qpose2)]
+    for ms in (False, True):
+        batch = est.forward_batch(items, neighborhood=15, layer=2, mask_scores=ms)
+        for it, got in zip(items, batch):
+            want = est.forward_fine(it["proposal"], pm, None, mesh_full, K, bbox, it["est_scale"], it["prev_pose"],
+                                    neighborhood=15, layer=2, mask_scores=ms)
+            assert torch.equal(got["all_scores"], want["all_scores"])
+            assert np.array_equal(got["TCO"][0], want["TCO"][0]) and float(got["scores"][0]) == float(want["scores"][0])
 
 
 def test_full_size_determinism_and_duplicates(lib, sd2):
