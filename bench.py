@@ -233,7 +233,7 @@ def parity_block(est, mesh, args, n: int):
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     from freepose_b200 import _lib
-    from freepose_b200.distributed import ScoreGather, init_from_env
+    from freepose_b200.distributed import PeerScoreGather, ScoreGather, init_from_env
     from freepose_b200.pipeline.estimators.pose_estimator import DinoPoseEstimator
     from freepose_b200.synthetic import synthetic_mesh
     from freepose_b200.vit_weights import synthetic_state_dict
@@ -267,7 +267,8 @@ def run_b200(args):
     bbox = np.array([200.0, 150.0, 330.0, 290.0])
     # strong: ONE gather buffer of args.hyp scores, each rank fills its shard.  weak: the ranks' proposals are
     # independent -- nothing is exchanged per step; one gather of every rank's scores closes the timed region.
-    sg = ScoreGather(args.hyp if strong else args.hyp * world, world, dev, rank=rank)
+    peer = strong and world > 1 and args.exchange == "p2p"
+    sg = (PeerScoreGather if peer else ScoreGather)(args.hyp if strong else args.hyp * world, world, dev, rank=rank)
     shard = (rank, world, sg) if (strong and world > 1) else None
 
     def step_device():
@@ -293,7 +294,7 @@ def run_b200(args):
     # ---- warm-up, then the device-resident timed region (value) with live per-kernel events
     for _ in range(max(args.warmup, 3)):
         last = step_device()
-    if world > 1:
+    if world > 1 and not peer:
         sg.gather(rank)                                    # NCCL sets its transports up lazily at the first collective
     barrier()
     lib.fp_profile_reset()
@@ -406,6 +407,9 @@ def run_b200(args):
            "kernel_time_share_of_step": total_kernel_ms / args.steps / ms_per_step,
            "best_hypothesis": int(res_e2e["top_indices"][0])}
     if strong:
+        strong_check["exchange"] = ("peer memory: fp_score_publish stores into every rank's buffer over NVLink, "
+                                    "fp_topk_after_exchange waits on the device" if peer else
+                                    "fp_allgather_scores (NCCL from the C ABI)") if world > 1 else "none (one GPU)"
         out["strong_scaling"] = strong_check
         out["latency_ms_per_proposal"] = ms_per_step
     if world == 1 and not args.no_cpu_baseline:
@@ -702,6 +706,8 @@ def main():
     ap.add_argument("--per-proposal", action="store_true",
                     help="video: one estimator call per proposal (the reference's loop) instead of forward_batch per frame")
     ap.add_argument("--batch", type=int, default=None, help="ffa: renders per batch (256); refiner: renders per frame (64)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="strong scaling: how the scores travel (peer-memory stores fused into the score kernel, or NCCL)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one proposal per GPU per step; strong: one proposal, hypotheses sharded over the GPUs")
     args = ap.parse_args()

@@ -85,6 +85,13 @@ SIGNATURES = {
     "fp_comm_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
     "fp_allgather_scores": (_i, [_vp, _vp, _i, _vp]),
     "fp_comm_destroy": (_i, [_vp]),
+    "fp_exchange_bytes": (_sz, [_i, _i]),
+    "fp_p2p_alloc": (_i, [_sz, C.POINTER(_vp), _vp]),
+    "fp_p2p_open": (_i, [_vp, C.POINTER(_vp)]),
+    "fp_p2p_close": (_i, [_vp]),
+    "fp_p2p_free": (_i, [_vp]),
+    "fp_score_publish": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, C.c_uint, _vp, _sz, _vp]),
+    "fp_topk_after_exchange": (_i, [_vp, _i, _i, _i, C.c_uint, _i, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -180,4 +180,23 @@ FP_API int fp_allgather_scores(void* comm, float* scores, int per_rank, void* st
 }
 FP_API int fp_comm_destroy(void* comm) { return fp::comm_destroy(comm); }
 
+FP_API size_t fp_exchange_bytes(int world, int per_rank) { return fp::exchange_bytes(world, per_rank); }
+FP_API int fp_p2p_alloc(size_t bytes, void** ptr, fp_p2p_handle* handle) { return fp::p2p_alloc(bytes, ptr, handle); }
+FP_API int fp_p2p_open(const fp_p2p_handle* handle, void** ptr) { return fp::p2p_open(handle, ptr); }
+FP_API int fp_p2p_close(void* ptr) { return fp::p2p_close(ptr); }
+FP_API int fp_p2p_free(void* ptr) { return fp::p2p_free(ptr); }
+FP_API int fp_score_publish(const void* feats_t, const void* feat_q, const float* weights, int B, int P, int D,
+                            int normalise_query, void* const* peers, void* own_buffer, int rank, int world, int per_rank,
+                            unsigned epoch, void* publish_workspace, size_t workspace_bytes, void* stream) {
+  return fp::score_publish(B16(feats_t), B16(feat_q), weights, B, P, D, normalise_query,
+                           reinterpret_cast<float* const*>(peers), reinterpret_cast<float*>(own_buffer), rank, world, per_rank,
+                           epoch, publish_workspace, workspace_bytes, S(stream));
+}
+FP_API int fp_topk_after_exchange(void* own_buffer, int world, int per_rank, int n_total, unsigned epoch, int k,
+                                  int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  return fp::topk_after_exchange(reinterpret_cast<float*>(own_buffer), world, per_rank, n_total, epoch, k, topk_idx, topk_val,
+                                 workspace, workspace_bytes, S(stream));
+}
+
 }  // extern "C"

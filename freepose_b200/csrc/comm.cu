@@ -102,6 +102,36 @@ int comm_allgather_scores(void* comm, float* scores, int per_rank, cudaStream_t 
   return 0;
 }
 
+// ---- peer memory through CUDA IPC (one process per GPU on one node: NVLink / NVSwitch peer access) --------------------
+int p2p_alloc(size_t bytes, void** ptr, void* handle64) {
+  FP_REQUIRE(ptr && handle64 && bytes > 0, "p2p_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  FP_CUDA(cudaMalloc(&p, bytes));
+  FP_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return 0;
+}
+int p2p_open(const void* handle64, void** ptr) {
+  FP_REQUIRE(ptr && handle64, "p2p_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  FP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int p2p_close(void* ptr) {
+  if (ptr) FP_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+int p2p_free(void* ptr) {
+  if (ptr) FP_CUDA(cudaFree(ptr));
+  return 0;
+}
+
 int comm_destroy(void* comm) {
   if (!comm) return 0;
   Comm* c = reinterpret_cast<Comm*>(comm);

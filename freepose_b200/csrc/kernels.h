@@ -75,6 +75,17 @@ int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, in
 size_t score_workspace_bytes(int B, int P, int D);
 int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val, void* workspace,
               size_t workspace_bytes, cudaStream_t stream);
+// peer-memory exchange of the scores (score.cu: PeerExchange)
+size_t exchange_bytes(int world, int per_rank);
+int score_publish(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D, int normalise_query,
+                  float* const* peers_dev, float* own_buffer, int rank, int world, int per_rank, unsigned epoch,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int topk_after_exchange(float* own_buffer, int world, int per_rank, int n_total, unsigned epoch, int k, int* topk_idx,
+                        float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int p2p_alloc(size_t bytes, void** ptr, void* handle64);
+int p2p_open(const void* handle64, void** ptr);
+int p2p_close(void* ptr);
+int p2p_free(void* ptr);
 
 // FFA pooling (reference extract_retrieval_features.py:49-57)
 int ffa_pool(const bf16* feats, const uint8_t* masks, int V, int res, int g, int D, float* out,

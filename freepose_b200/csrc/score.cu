@@ -54,9 +54,24 @@ prep_query_kernel(const bf16* __restrict__ q, bf16* __restrict__ qn, int P, int 
     }
 }
 
+// Peer-memory exchange (fp_score_publish): the score kernel itself is the "send" side of the
+// all-gather.  Every rank owns an exchange buffer [2 parities][world * per_rank scores | world flags] that its peers map
+// through CUDA IPC; a score is stored into the slot (rank * per_rank + b) of EVERY rank's buffer over NVLink as it is
+// produced, and the last CTA to finish publishes "rank r is complete for this epoch" in every buffer.  The receiving
+// side is the top-k kernel, which waits for the world flags of its own buffer.  No collective call, no extra kernel.
+struct PeerExchange {
+  float* const* peers;      // device array [world]: the ranks' exchange buffers (this rank's own included), or nullptr
+  int world, rank, per_rank;
+  unsigned epoch;           // increases by one per exchange; parity selects the half of the buffer
+  unsigned* done;           // device counter of finished CTAs (this rank's, zero between launches)
+};
+__host__ __device__ inline size_t exchange_half_floats(int world, int per_rank) {
+  return (size_t(world) * per_rank + size_t(world) + 63) / 64 * 64;     // scores, then one flag per rank; 256-byte multiple
+}
+
 __global__ void __launch_bounds__(SC_WARPS * 32)
 score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, const float* __restrict__ weights,
-             int P, int D, float* __restrict__ scores, float* __restrict__ patch_scores) {
+             int P, int D, float* __restrict__ scores, float* __restrict__ patch_scores, const PeerExchange px) {
   extern __shared__ float s_patch[];  // [P] bf16-valued per-patch cosines
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
@@ -109,6 +124,12 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
       for (int n = lane; n < P; n += 32) acc = __fadd_rn(acc, s_patch[n]);
       acc = warp_sum(acc);
       if (lane == 0) scores[b] = bf16_round(__fdiv_rn(acc, float(P)));
+      if (px.peers != nullptr && lane < px.world) {
+        // the same value into this rank's slot of every rank's buffer (lane r -> rank r; one NVLink store each)
+        const float v = bf16_round(__fdiv_rn(acc, float(P)));
+        float* dst = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
+        dst[size_t(px.rank) * px.per_rank + b] = v;
+      }
     } else {
       const float* w = weights + size_t(b) * P;
       float num = 0.f, den = 0.f;
@@ -120,6 +141,31 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
       num = warp_sum(num);
       den = warp_sum(den);
       if (lane == 0) scores[b] = __fdiv_rn(num, den);
+      if (px.peers != nullptr && lane < px.world) {
+        float* dst = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
+        dst[size_t(px.rank) * px.per_rank + b] = __fdiv_rn(num, den);
+      }
+    }
+    if (px.peers != nullptr) {
+      // publish: stores above -> system-scope fence -> count this CTA; the last CTA raises this rank's flag everywhere
+      __threadfence_system();
+      __syncwarp();
+      unsigned last = 0;
+      if (lane == 0) {
+        __threadfence_system();
+        last = atomicAdd(px.done, 1u) == gridDim.x - 1;
+        __threadfence_system();
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence_system();
+        if (lane == 0) *px.done = 0;
+        if (lane < px.world) {
+          float* half = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
+          unsigned* flags = reinterpret_cast<unsigned*>(half + size_t(px.world) * px.per_rank);
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags + px.rank), "r"(px.epoch) : "memory");
+        }
+      }
     }
   }
 }
@@ -134,10 +180,23 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
 
 __global__ void __launch_bounds__(1024)
 topk_kernel(const float* __restrict__ scores, int B, int k, int* __restrict__ idx_out, float* __restrict__ val_out,
-            uint8_t* __restrict__ taken) {
+            uint8_t* __restrict__ taken, const unsigned* __restrict__ wait_flags, int wait_world, unsigned wait_epoch) {
   __shared__ float sv[32];
   __shared__ int si[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (wait_flags != nullptr) {
+    // receiving side of the peer-memory exchange: every rank's flag must have reached this epoch (bounded spin: a
+    // protocol bug or a dead peer traps instead of hanging the device)
+    if (threadIdx.x < wait_world) {
+      unsigned v, spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+        if (int(v - wait_epoch) >= 0) break;
+        if (++spins > (1u << 25)) __trap();      // ~10 s of polling
+      } while (true);
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < B; i += blockDim.x) taken[i] = 0;
   __syncthreads();
   for (int r = 0; r < k; ++r) {
@@ -242,12 +301,57 @@ int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, in
   FP_CUDA(cudaGetLastError());
   const size_t smem = size_t(P) * sizeof(float);
   FP_REQUIRE(smem <= 48 * 1024, "score: P=%d too large", P);
-  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, scores_out, patch_scores_out);
+  PeerExchange none{};
+  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, scores_out, patch_scores_out, none);
   FP_CUDA(cudaGetLastError());
   if (k > 0) {
-    topk_kernel<<<1, 1024, 0, stream>>>(scores_out, B, k, topk_idx, topk_val, taken);
+    topk_kernel<<<1, 1024, 0, stream>>>(scores_out, B, k, topk_idx, topk_val, taken, nullptr, 0, 0u);
     FP_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+size_t exchange_bytes(int world, int per_rank) { return 2 * exchange_half_floats(world, per_rank) * sizeof(float) + 256; }
+
+// scores of this rank's B (<= per_rank) hypotheses -> slot `rank` of every rank's exchange buffer + completion flags.
+// `peers` = device array of the world buffer pointers; own buffer = peers[rank] as seen by this process.
+int score_publish(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D, int normalise_query,
+                  float* const* peers_dev, float* own_buffer, int rank, int world, int per_rank, unsigned epoch,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(D % 256 == 0 && D <= 256 * MAX_CHUNKS, "score: D=%d must be a multiple of 256 and <= 1024", D);
+  FP_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "publish: rank %d / world %d (at most 32 ranks)", rank, world);
+  FP_REQUIRE(B > 0 && B <= per_rank && P > 0, "publish: B=%d must be in [1, %d] (every rank needs at least one hypothesis)", B, per_rank);
+  FP_REQUIRE(workspace_bytes >= score_workspace_bytes(B, P, D) + 256, "publish: workspace too small");
+  FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "score: workspace must be 16-byte aligned");
+  FP_REQUIRE(peers_dev != nullptr && own_buffer != nullptr, "publish: null exchange buffers");
+  const size_t smem = size_t(P) * sizeof(float);
+  FP_REQUIRE(smem <= 48 * 1024, "score: P=%d too large", P);
+  bf16* qn = reinterpret_cast<bf16*>(workspace);
+  // the CTA counter lives behind the query copy and the top-k scratch in the workspace: the caller keeps this workspace
+  // across calls and zeroes it once (the last CTA of every launch resets the counter)
+  unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(workspace) + (score_workspace_bytes(B, P, D) + 15) / 16 * 16);
+  PeerExchange px{peers_dev, world, rank, per_rank, epoch, done};
+  float* local = own_buffer + (epoch & 1u) * exchange_half_floats(world, per_rank) + size_t(rank) * per_rank;
+  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, 2, stream);
+  prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query);
+  FP_CUDA(cudaGetLastError());
+  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, local, nullptr, px);
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// receiving side: waits for all ranks' flags of `epoch` in this rank's own buffer, then the deterministic top-k over
+// the first n_total slots
+int topk_after_exchange(float* own_buffer, int world, int per_rank, int n_total, unsigned epoch, int k, int* topk_idx,
+                        float* topk_val, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  FP_REQUIRE(n_total > 0 && n_total <= world * per_rank && k > 0 && k <= n_total, "topk_after_exchange: bad sizes");
+  FP_REQUIRE(workspace_bytes >= size_t(n_total), "topk: workspace too small");
+  float* half = own_buffer + (epoch & 1u) * exchange_half_floats(world, per_rank);
+  const unsigned* flags = reinterpret_cast<const unsigned*>(half + size_t(world) * per_rank);
+  ProfScope prof(PROF_SCORE, double(n_total) * 4, 1, stream);
+  topk_kernel<<<1, 1024, 0, stream>>>(half, n_total, k, topk_idx, topk_val, reinterpret_cast<uint8_t*>(workspace), flags, world,
+                                      epoch);
+  FP_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -257,7 +361,7 @@ int topk_only(const float* scores, int B, int k, int* topk_idx, float* topk_val,
   FP_REQUIRE(workspace_bytes >= size_t(B), "topk: workspace too small");
   if (k == 0) return 0;
   ProfScope prof(PROF_SCORE, double(B) * 4, 1, stream);
-  topk_kernel<<<1, 1024, 0, stream>>>(scores, B, k, topk_idx, topk_val, reinterpret_cast<uint8_t*>(workspace));
+  topk_kernel<<<1, 1024, 0, stream>>>(scores, B, k, topk_idx, topk_val, reinterpret_cast<uint8_t*>(workspace), nullptr, 0, 0u);
   FP_CUDA(cudaGetLastError());
   return 0;
 }

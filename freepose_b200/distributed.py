@@ -88,6 +88,109 @@ class ScoreGather:
             self._lib.fp_comm_destroy(self._comm)
             self._comm = None
 
+    # -- the two calls the estimators make (overridden by PeerScoreGather) ----------------------------------------
+    def score_into(self, rank: int, feats_t: torch.Tensor, feat_q: torch.Tensor) -> None:
+        """Scores of this rank's hypotheses, written straight into its slice of the gather buffer."""
+        from . import ops
+        ops.score_topk(feats_t, feat_q, k=0, scores_out=self.local_view(rank))
+
+    def gather_topk(self, rank: int, k: int):
+        """-> (all n scores, top-k indices, top-k values), identical on every rank."""
+        from . import ops
+        scores = self.gather(rank)
+        idx, val = ops.topk(scores, k)
+        return scores, idx, val
+
+
+class _DeviceMemory:
+    """Raw device memory as a CUDA array (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerScoreGather(ScoreGather):
+    """The same exchange over PEER MEMORY instead of a collective call (one node, NVLink / NVSwitch): every rank's
+    exchange buffer is mapped into every process through CUDA IPC; ``fp_score_publish`` -- the score kernel -- stores each
+    score into slot (rank, b) of every rank's buffer as it is produced and its last CTA raises this rank's flag in every
+    buffer; ``fp_topk_after_exchange`` waits on the device for the world flags of the own buffer and runs the top-k.
+    Two launches per proposal on the exchange path (score + top-k), no NCCL call, nothing on the host."""
+
+    def __init__(self, n_total: int, world: int, device, rank: int | None = None):
+        import ctypes as C
+        from . import _lib
+        self.n, self.world = n_total, world
+        self.per = -(-n_total // world)
+        self.device = torch.device(device)
+        self.rank = dist.get_rank() if rank is None else rank
+        self._lib = lib = _lib.load()
+        self._comm = None
+        self.epoch = 0
+        nbytes = lib.fp_exchange_bytes(world, self.per)
+        own, handle = C.c_void_p(), (C.c_char * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.fp_p2p_alloc(nbytes, C.byref(own), handle), "fp_p2p_alloc")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle))
+            self._peer_ptrs = []
+            for r in range(world):
+                if r == self.rank:
+                    self._peer_ptrs.append(own.value)
+                else:
+                    p = C.c_void_p()
+                    _lib.check(lib.fp_p2p_open((C.c_char * 64).from_buffer_copy(handles[r]), C.byref(p)), "fp_p2p_open")
+                    self._peer_ptrs.append(p.value)
+        self._own = own.value
+        self._peers_dev = torch.tensor(self._peer_ptrs, dtype=torch.int64, device=self.device)
+        self._half = (nbytes - 256) // 8                       # floats per parity half
+        self._view = torch.as_tensor(_DeviceMemory(self._own, 2 * self._half), device=self.device)
+        self._ws = {}
+        dist.barrier()                                         # every buffer is mapped (and zeroed) before the first publish
+
+    def _publish_ws(self, B, P, D):
+        key = (B, P, D)
+        if key not in self._ws:
+            n = self._lib.fp_score_workspace_bytes(B, P, D) + 512
+            self._ws[key] = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        return self._ws[key]
+
+    def score_into(self, rank, feats_t, feat_q):
+        from . import _lib
+        B, P, D = feats_t.shape
+        feat_q = feat_q.reshape(P, D)
+        ws = self._publish_ws(B, P, D)
+        self.epoch += 1
+        _lib.check(self._lib.fp_score_publish(_lib.ptr(feats_t), _lib.ptr(feat_q), None, B, P, D, 1, _lib.ptr(self._peers_dev),
+                                              self._own, self.rank, self.world, self.per, self.epoch, _lib.ptr(ws),
+                                              ws.numel(), _lib.stream_ptr()), "fp_score_publish")
+
+    def gather_topk(self, rank, k):
+        from . import _lib
+        idx = torch.empty(k, dtype=torch.int32, device=self.device)
+        val = torch.empty(k, dtype=torch.float32, device=self.device)
+        ws = torch.empty(max(self.n, 256), dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.fp_topk_after_exchange(self._own, self.world, self.per, self.n, self.epoch, k, _lib.ptr(idx),
+                                                    _lib.ptr(val), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "fp_topk_after_exchange")
+        half = self._view[(self.epoch & 1) * self._half:]
+        return half[:self.n].clone(), idx, val                 # a copy: the half is rewritten two exchanges later
+
+    def local_view(self, rank):
+        raise RuntimeError("PeerScoreGather has no host-visible local slice: use score_into / gather_topk")
+
+    def gather(self, rank):
+        raise RuntimeError("PeerScoreGather exchanges inside score_into / gather_topk")
+
+    def close(self):
+        if getattr(self, "_own", None):
+            torch.cuda.synchronize(self.device)
+            dist.barrier()                                     # nobody still stores into a buffer that is about to go
+            for r, p in enumerate(self._peer_ptrs):
+                if r != self.rank:
+                    self._lib.fp_p2p_close(p)
+            self._lib.fp_p2p_free(self._own)
+            self._own = None
+
 
 def stable_topk_host(scores: torch.Tensor, k: int):
     """Deterministic CPU top-k (descending, ties -> lowest index): used on gloo/CPU ranks in tests; GPUs use fp_topk."""

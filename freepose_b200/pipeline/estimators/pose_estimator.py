@@ -217,9 +217,8 @@ class DinoPoseEstimator(nn.Module):
         lo, hi = shard_bounds(n, rank, world)
         if hi > lo:
             feats, _, _, query_feat = self.render_features(mesh, P_all[lo:hi], layer=layer, query=proposal)
-            ops.score_topk(feats, query_feat, k=0, scores_out=sg.local_view(rank))
-        scores = sg.gather(rank)
-        top_idx, top_val = ops.topk(scores, k)
+            sg.score_into(rank, feats, query_feat)
+        scores, top_idx, top_val = sg.gather_topk(rank, k)
         # winners' depth maps for the translation: the k winning poses are gathered ON THE DEVICE and re-rasterised on
         # every rank (k renders instead of a second collective; no host round trip)
         _, depth = self.renderer.render_device(mesh, P_all[top_idx.long()])

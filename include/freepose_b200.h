@@ -253,6 +253,28 @@ FP_API int fp_comm_create(const fp_comm_id* id /* host */, int rank, int world, 
 FP_API int fp_allgather_scores(void* comm, float* scores, int per_rank, void* stream);
 FP_API int fp_comm_destroy(void* comm);
 
+/* The same exchange WITHOUT a collective call: peer memory over NVLink (CUDA IPC; one process per GPU on one node).
+ * Every rank owns an exchange buffer of fp_exchange_bytes(world, per_rank) that it allocates with fp_p2p_alloc and whose
+ * 64-byte handle the host hands to the other ranks, which map it with fp_p2p_open.  fp_score_publish is fp_score_topk's
+ * score stage with the all-gather fused in: each score is stored into slot (rank, b) of EVERY rank's buffer as it is
+ * produced, and the last CTA raises this rank's flag in every buffer.  fp_topk_after_exchange waits (on the device) for
+ * the world flags of the own buffer and runs the deterministic top-k.  `epoch` must increase by one per exchange on all
+ * ranks (its parity selects one of two halves of the buffer, so a rank may run one exchange ahead of a peer).
+ * peers: DEVICE array of `world` pointers (own buffer included, as mapped in this process); publish_workspace:
+ * fp_score_workspace_bytes(B,P,D) + 256 bytes, kept by the caller across calls and zeroed once. */
+typedef struct fp_p2p_handle { char bytes[64]; } fp_p2p_handle;
+FP_API size_t fp_exchange_bytes(int world, int per_rank);
+FP_API int fp_p2p_alloc(size_t bytes, void** ptr /* host out */, fp_p2p_handle* handle /* host out */);
+FP_API int fp_p2p_open(const fp_p2p_handle* handle /* host */, void** ptr /* host out */);
+FP_API int fp_p2p_close(void* ptr);
+FP_API int fp_p2p_free(void* ptr);
+FP_API int fp_score_publish(const void* feats_t, const void* feat_q, const float* weights, int B, int P, int D,
+                            int normalise_query, void* const* peers, void* own_buffer, int rank, int world, int per_rank,
+                            unsigned epoch, void* publish_workspace, size_t workspace_bytes, void* stream);
+FP_API int fp_topk_after_exchange(void* own_buffer, int world, int per_rank, int n_total, unsigned epoch, int k,
+                                  int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,16 +57,18 @@ def test_b200_arm_parity_block_and_cpu_baseline():
 
 
 @pytest.mark.gpu
-def test_b200_arm_strong_scaling_two_gpus():
-    """--scaling strong under torchrun: hypotheses of one proposal sharded over 2 ranks, fp_allgather_scores (NCCL from
-    the C ABI), top-k after the gather, identical on both ranks and equal to the single-GPU result."""
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_b200_arm_strong_scaling_two_gpus(exchange):
+    """--scaling strong under torchrun: hypotheses of one proposal sharded over 2 ranks; the scores travel either through
+    peer memory (fp_score_publish / fp_topk_after_exchange) or through fp_allgather_scores (NCCL from the C ABI); top-k
+    after the exchange, identical on both ranks and equal to the single-GPU result."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(ROOT / "bench.py"), "--gpus", "2",
-                        "--scaling", "strong", "--steps", "2", "--warmup", "3", "--hyp", "33", "--chunk", "34",
-                        "--layer", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--scaling", "strong", "--exchange", exchange, "--steps", "2", "--warmup", "3", "--hyp", "33",
+                        "--chunk", "34", "--layer", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert d["scaling"] == "strong" and d["n_gpus"] == 2

@@ -357,6 +357,7 @@ def test_hypothesis_sharded_forward_equals_unsharded(small_setup):
     """the hypotheses of ONE proposal split contiguously over W ranks, scores written
     into the gather buffer, top-k AFTER the gather.  Emulated on one GPU: the W 'ranks' run one after the other on the
     same buffer (the collective is then the identity), for W that do and do not divide the 24 hypotheses."""
+    from freepose_b200 import ops
     from freepose_b200.distributed import shard_bounds
     mesh, est, _, query, _ = small_setup
     K = np.array([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
@@ -373,6 +374,13 @@ def test_hypothesis_sharded_forward_equals_unsharded(small_setup):
 
         def gather(self, rank):
             return self.buf[:self.n]
+
+        def score_into(self, rank, feats, qf):
+            ops.score_topk(feats, qf, k=0, scores_out=self.local_view(rank))
+
+        def gather_topk(self, rank, k):
+            idx, val = ops.topk(self.buf[:self.n], k)
+            return self.buf[:self.n], idx, val
 
     for world in (2, 5, 8):
         sg = InProcessGather(24, world)
