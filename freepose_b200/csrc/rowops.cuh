@@ -30,7 +30,7 @@ __device__ __forceinline__ float row_norm(const uint4 (&u)[MAX_CHUNKS], int chun
       float f[8];
       unpack8(u[c], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, __fmul_rn(f[j], f[j]));
+      for (int j = 0; j < 8; ++j) acc = fmaf(f[j], f[j], acc);  // == fadd(acc, fmul(x, x)): the square of a bf16 is exact in fp32
     }
   acc = warp_sum(acc);
   const float nrm = bf16_round(__fsqrt_rn(acc));

@@ -11,7 +11,8 @@
 //   * a D-long reduction: lane l accumulates elements c*256 + l*8 + j (c outer, j = 0..7 inner) with
 //     acc = acc + a*b (a*b is exact in fp32 for bf16 inputs), then the xor-butterfly 16,8,4,2,1;
 //   * a P-long reduction: lane l accumulates n = l, l+32, ... ascending, then the same butterfly.
-// HBM-bound: every template token row (2 KB) is read exactly once; one CTA per hypothesis.
+// HBM-bound: every template token row (2 KB) is read exactly once (score_rows_kernel), the per-patch cosines take a
+// second, tiny pass (score_reduce_kernel).
 #include "common.cuh"
 #include "kernels.h"
 #include "rowops.cuh"
@@ -20,13 +21,18 @@ namespace fp {
 
 namespace {
 
-constexpr int SC_WARPS = 16;   // 512 threads per hypothesis: two rows per warp in flight = 64 KB per CTA
+constexpr int SC_WARPS = 16;        // prep_query: one warp per query row
+constexpr int ROW_WARPS = 8;        // rows kernel: 256 threads, two CTAs per SM
+constexpr int ROWS_PER_ITEM = 4;    // hypotheses per work item: 4 x 2 KB template rows in flight per warp
+constexpr int RED_WARPS = 8;        // reduce kernel: one warp per hypothesis
 using namespace rowops;
 
-// qn = normalised (or verbatim) query tokens, one warp per row
+// qn = normalised (or verbatim) query tokens, one warp per row; also zeroes the rows kernel's work counter
 __global__ void __launch_bounds__(SC_WARPS * 32)
-prep_query_kernel(const bf16* __restrict__ q, bf16* __restrict__ qn, int P, int D, int normalise) {
+prep_query_kernel(const bf16* __restrict__ q, bf16* __restrict__ qn, int P, int D, int normalise,
+                  unsigned* __restrict__ counter) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
   const int n = blockIdx.x * SC_WARPS + warp;
   if (n >= P) return;
   const int chunks = D / 256;
@@ -54,7 +60,7 @@ prep_query_kernel(const bf16* __restrict__ q, bf16* __restrict__ qn, int P, int 
     }
 }
 
-// Peer-memory exchange (fp_score_publish): the score kernel itself is the "send" side of the
+// Peer-memory exchange (fp_score_publish): the score stage itself is the "send" side of the
 // all-gather.  Every rank owns an exchange buffer [2 parities][world * per_rank scores | world flags] that its peers map
 // through CUDA IPC; a score is stored into the slot (rank * per_rank + b) of EVERY rank's buffer over NVLink as it is
 // produced, and the last CTA to finish publishes "rank r is complete for this epoch" in every buffer.  The receiving
@@ -69,87 +75,103 @@ __host__ __device__ inline size_t exchange_half_floats(int world, int per_rank) 
   return (size_t(world) * per_rank + size_t(world) + 63) / 64 * 64;     // scores, then one flag per rank; 256-byte multiple
 }
 
-__global__ void __launch_bounds__(SC_WARPS * 32)
-score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, const float* __restrict__ weights,
-             int P, int D, float* __restrict__ scores, float* __restrict__ patch_scores, const PeerExchange px) {
-  extern __shared__ float s_patch[];  // [P] bf16-valued per-patch cosines
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
+// Stage 1, HBM-bound: per-patch cosines s[b][n] = bf16(sum_d bf16(t/|t|) * qn).  Work item = (patch n, 4 consecutive
+// hypotheses): the warp issues the four 2 KB template rows at once (8 KB in flight per warp, 16 warps per SM), reads
+// the query row n once for the four, and takes its next item from a global counter -- no tail, whatever B is.
+//
+// tn = bf16(t / nrm) is evaluated as bf16(t * fl(1/nrm)) -- the same value, always: t and nrm are bf16 (8-bit
+// significands T, N), a bf16 rounding boundary is m * 2^k with m an odd 9-bit integer, and T * 2^c = N * m has no
+// solution (m is odd and m > T), so |t/nrm - boundary| >= boundary / (N * m) > 2^-17 relative, while the reciprocal and
+// the product together err by < 2^-22 (tests/test_oracle_golden.py::test_reciprocal_normalisation_is_exact runs all
+// significand pairs).
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
+score_rows_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, int B, int P, int D,
+                  float* __restrict__ patch, unsigned* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
   const int chunks = D / 256;
-  const bf16* base = feats_t + size_t(b) * P * D;
-  // HBM-bound: keep the NEXT row of this warp in flight while the current one is reduced (one row per warp in flight left
-  // the kernel at 1.6 TB/s: load -> dependent reduction -> load)
-  uint4 tn_[MAX_CHUNKS], qn_[MAX_CHUNKS];
-  if (warp < P) {
-    load_row(base + size_t(warp) * D, lane, chunks, tn_);
-    load_row(qn + size_t(warp) * D, lane, chunks, qn_);
-  }
-  for (int n = warp; n < P; n += SC_WARPS) {
-    uint4 t[MAX_CHUNKS], q[MAX_CHUNKS];
+  const unsigned total = unsigned((B + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM) * unsigned(P);
+  for (;;) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    const int g = int(item / unsigned(P)), n = int(item - unsigned(g) * unsigned(P));
+    const int b0 = g * ROWS_PER_ITEM;
+    uint4 t[ROWS_PER_ITEM][MAX_CHUNKS];
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c) { t[c] = tn_[c]; q[c] = qn_[c]; }
-    if (n + SC_WARPS < P) {
-      load_row(base + size_t(n + SC_WARPS) * D, lane, chunks, tn_);
-      load_row(qn + size_t(n + SC_WARPS) * D, lane, chunks, qn_);
+    for (int r = 0; r < ROWS_PER_ITEM; ++r)
+      if (b0 + r < B) load_row(feats_t + (size_t(b0 + r) * P + n) * D, lane, chunks, t[r]);
+    float qf[MAX_CHUNKS][8];
+    {
+      uint4 qv[MAX_CHUNKS];
+      load_row(qn + size_t(n) * D, lane, chunks, qv);
+#pragma unroll
+      for (int c = 0; c < MAX_CHUNKS; ++c)
+        if (c < chunks) unpack8(qv[c], qf[c]);
     }
-    const float nrm = row_norm(t, chunks);
-    const float rnrm = __frcp_rn(nrm);
-    float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAX_CHUNKS; ++c)
-      if (c < chunks) {
-        float tf[8], qf[8];
-        unpack8(t[c], tf);
-        unpack8(q[c], qf);
+    for (int r = 0; r < ROWS_PER_ITEM; ++r) {
+      if (b0 + r >= B) break;
+      const float rnrm = __frcp_rn(row_norm(t[r], chunks));
+      float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // tn = bf16(t / nrm), the reference's rounding, without an IEEE division per element: q = t * (1/nrm) is
-          // within 2 fp32 ulps of the correctly rounded quotient, so unless q sits within 64 ulps of a bf16 rounding
-          // midpoint (0.4 % of the values) both round to the same bf16; the rest take the exact division.
-          const float qd = __fmul_rn(tf[j], rnrm);
-          const int low = int(__float_as_uint(qd) & 0xffffu) - 0x8000;
-          const float tn = (low > 64 || low < -64) ? bf16_round(qd) : bf16_round(__fdiv_rn(tf[j], nrm));
-          acc = __fadd_rn(acc, __fmul_rn(tn, qf[j]));
+      for (int c = 0; c < MAX_CHUNKS; ++c)
+        if (c < chunks) {
+          float tf[8];
+          unpack8(t[r][c], tf);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const uint32_t tn = pack_bf16x2(__fmul_rn(tf[j], rnrm), __fmul_rn(tf[j + 1], rnrm));
+            acc = fmaf(bf16lo(tn), qf[c][j], acc);          // == fadd(acc, fmul(tn, q)): the product is exact in fp32
+            acc = fmaf(bf16hi(tn), qf[c][j + 1], acc);
+          }
         }
-      }
-    acc = warp_sum(acc);
-    if (lane == 0) s_patch[n] = bf16_round(acc);
+      acc = warp_sum(acc);
+      if (lane == 0) patch[size_t(b0 + r) * P + n] = bf16_round(acc);
+    }
   }
-  __syncthreads();
-  if (patch_scores != nullptr)
-    for (int n = threadIdx.x; n < P; n += blockDim.x) patch_scores[size_t(b) * P + n] = s_patch[n];
-  if (warp == 0) {
+}
+
+// Stage 2: one warp per hypothesis reduces its P per-patch cosines (fixed order: lane l sums n = l, l+32, ... ascending,
+// then the butterfly) to the score -- mean in bf16, or the mask-weighted mean in fp32 -- and, on the exchange path,
+// stores it into every rank's buffer; the last CTA raises this rank's flags.
+__global__ void __launch_bounds__(RED_WARPS * 32)
+score_reduce_kernel(const float* __restrict__ patch, const float* __restrict__ weights, int B, int P,
+                    float* __restrict__ scores, const PeerExchange px) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * RED_WARPS + warp;
+  if (b < B) {
+    const float* s = patch + size_t(b) * P;
+    float v;
     if (weights == nullptr) {
       float acc = 0.f;
-      for (int n = lane; n < P; n += 32) acc = __fadd_rn(acc, s_patch[n]);
+      for (int n = lane; n < P; n += 32) acc = __fadd_rn(acc, s[n]);
       acc = warp_sum(acc);
-      if (lane == 0) scores[b] = bf16_round(__fdiv_rn(acc, float(P)));
-      if (px.peers != nullptr && lane < px.world) {
-        // the same value into this rank's slot of every rank's buffer (lane r -> rank r; one NVLink store each)
-        const float v = bf16_round(__fdiv_rn(acc, float(P)));
-        float* dst = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
-        dst[size_t(px.rank) * px.per_rank + b] = v;
-      }
+      v = bf16_round(__fdiv_rn(acc, float(P)));
     } else {
       const float* w = weights + size_t(b) * P;
       float num = 0.f, den = 0.f;
       for (int n = lane; n < P; n += 32) {
         const float wn = w[n];
-        num = __fadd_rn(num, __fmul_rn(s_patch[n], wn));
+        num = __fadd_rn(num, __fmul_rn(s[n], wn));
         den = __fadd_rn(den, wn);
       }
       num = warp_sum(num);
       den = warp_sum(den);
-      if (lane == 0) scores[b] = __fdiv_rn(num, den);
-      if (px.peers != nullptr && lane < px.world) {
-        float* dst = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
-        dst[size_t(px.rank) * px.per_rank + b] = __fdiv_rn(num, den);
-      }
+      v = __fdiv_rn(num, den);
     }
-    if (px.peers != nullptr) {
-      // publish: stores above -> system-scope fence -> count this CTA; the last CTA raises this rank's flag everywhere
-      __threadfence_system();
-      __syncwarp();
+    if (lane == 0) scores[b] = v;
+    if (px.peers != nullptr && lane < px.world) {
+      // the same value into this rank's slot of every rank's buffer (lane r -> rank r; one NVLink store each)
+      float* dst = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
+      dst[size_t(px.rank) * px.per_rank + b] = v;
+    }
+  }
+  if (px.peers != nullptr) {
+    // publish: stores above -> system-scope fence -> count this CTA; the last CTA raises this rank's flag everywhere
+    __threadfence_system();
+    __syncthreads();
+    if (warp == 0) {
       unsigned last = 0;
       if (lane == 0) {
         __threadfence_system();
@@ -158,7 +180,6 @@ score_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, cons
       }
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last) {
-        __threadfence_system();
         if (lane == 0) *px.done = 0;
         if (lane < px.world) {
           float* half = px.peers[lane] + (px.epoch & 1u) * exchange_half_floats(px.world, px.per_rank);
@@ -281,8 +302,30 @@ ffa_kernel(const bf16* __restrict__ feats, const uint8_t* __restrict__ masks, in
 
 }  // namespace
 
-size_t score_workspace_bytes(int B, int P, int D) {
-  return size_t(P) * D * sizeof(bf16) + size_t(B) + 256;
+// workspace: [query copy P*D bf16][top-k scratch B bytes][work counter][per-patch cosines B*P fp32]
+static size_t ws_taken_off(int P, int D) { return size_t(P) * D * sizeof(bf16); }
+static size_t ws_counter_off(int B, int P, int D) { return (ws_taken_off(P, D) + size_t(B) + 15) / 16 * 16; }
+static size_t ws_patch_off(int B, int P, int D) { return ws_counter_off(B, P, D) + 16; }
+size_t score_workspace_bytes(int B, int P, int D) { return ws_patch_off(B, P, D) + size_t(B) * P * sizeof(float) + 256; }
+
+// prep_query -> rows -> reduce on `stream`; scores_out[b] (and every peer's slot when px.peers is set)
+static int score_stages(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D,
+                        int normalise_query, float* scores_out, float* patch_scores_out, const PeerExchange& px,
+                        void* workspace, cudaStream_t stream) {
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  bf16* qn = reinterpret_cast<bf16*>(ws);
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + ws_counter_off(B, P, D));
+  float* patch = patch_scores_out ? patch_scores_out : reinterpret_cast<float*>(ws + ws_patch_off(B, P, D));
+  prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query, counter);
+  FP_CUDA(cudaGetLastError());
+  const long long items = (long long)((B + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM) * P;
+  const long long want = (items + ROW_WARPS - 1) / ROW_WARPS;
+  const int grid = int(want < 2LL * sm_count() ? want : 2LL * sm_count());
+  score_rows_kernel<<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, D, patch, counter);
+  FP_CUDA(cudaGetLastError());
+  score_reduce_kernel<<<(B + RED_WARPS - 1) / RED_WARPS, RED_WARPS * 32, 0, stream>>>(patch, weights, B, P, scores_out, px);
+  FP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, int B, int P, int D,
@@ -294,17 +337,12 @@ int score_topk(const bf16* feats_t, const bf16* feat_q, const float* weights, in
   FP_REQUIRE(workspace_bytes >= score_workspace_bytes(B, P, D), "score: workspace too small");
   FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "score: workspace must be 16-byte aligned");
   if (B == 0) return 0;
-  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, k > 0 ? 3 : 2, stream);
-  bf16* qn = reinterpret_cast<bf16*>(workspace);
-  uint8_t* taken = reinterpret_cast<uint8_t*>(workspace) + size_t(P) * D * sizeof(bf16);
-  prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query);
-  FP_CUDA(cudaGetLastError());
-  const size_t smem = size_t(P) * sizeof(float);
-  FP_REQUIRE(smem <= 48 * 1024, "score: P=%d too large", P);
+  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, k > 0 ? 4 : 3, stream);
   PeerExchange none{};
-  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, scores_out, patch_scores_out, none);
-  FP_CUDA(cudaGetLastError());
+  if (int rc = score_stages(feats_t, feat_q, weights, B, P, D, normalise_query, scores_out, patch_scores_out, none,
+                            workspace, stream)) return rc;
   if (k > 0) {
+    uint8_t* taken = reinterpret_cast<uint8_t*>(workspace) + ws_taken_off(P, D);
     topk_kernel<<<1, 1024, 0, stream>>>(scores_out, B, k, topk_idx, topk_val, taken, nullptr, 0, 0u);
     FP_CUDA(cudaGetLastError());
   }
@@ -324,20 +362,13 @@ int score_publish(const bf16* feats_t, const bf16* feat_q, const float* weights,
   FP_REQUIRE(workspace_bytes >= score_workspace_bytes(B, P, D) + 256, "publish: workspace too small");
   FP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "score: workspace must be 16-byte aligned");
   FP_REQUIRE(peers_dev != nullptr && own_buffer != nullptr, "publish: null exchange buffers");
-  const size_t smem = size_t(P) * sizeof(float);
-  FP_REQUIRE(smem <= 48 * 1024, "score: P=%d too large", P);
-  bf16* qn = reinterpret_cast<bf16*>(workspace);
-  // the CTA counter lives behind the query copy and the top-k scratch in the workspace: the caller keeps this workspace
+  // the CTA counter of the publish lives behind everything else in the workspace: the caller keeps this workspace
   // across calls and zeroes it once (the last CTA of every launch resets the counter)
   unsigned* done = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(workspace) + (score_workspace_bytes(B, P, D) + 15) / 16 * 16);
   PeerExchange px{peers_dev, world, rank, per_rank, epoch, done};
   float* local = own_buffer + (epoch & 1u) * exchange_half_floats(world, per_rank) + size_t(rank) * per_rank;
-  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, 2, stream);
-  prep_query_kernel<<<(P + SC_WARPS - 1) / SC_WARPS, SC_WARPS * 32, 0, stream>>>(feat_q, qn, P, D, normalise_query);
-  FP_CUDA(cudaGetLastError());
-  score_kernel<<<B, SC_WARPS * 32, smem, stream>>>(feats_t, qn, weights, P, D, local, nullptr, px);
-  FP_CUDA(cudaGetLastError());
-  return 0;
+  ProfScope prof(PROF_SCORE, (double(B) + 1) * P * D * 2, 3, stream);
+  return score_stages(feats_t, feat_q, weights, B, P, D, normalise_query, local, nullptr, px, workspace, stream);
 }
 
 // receiving side: waits for all ranks' flags of `epoch` in this rank's own buffer, then the deterministic top-k over

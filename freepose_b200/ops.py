@@ -316,11 +316,19 @@ def crop_resize_pad(src: torch.Tensor, boxes: torch.Tensor, target: int, to_patc
     return dst, status
 
 
+@functools.lru_cache(maxsize=256)
+def _kinv_device(k_bytes: bytes, dev_index: int) -> torch.Tensor:
+    """inv(K) on the device, uploaded once per intrinsic matrix (a blocking pageable copy per call would make the host
+    wait for everything queued on the stream -- the whole ViT forward in the per-frame loop)."""
+    K = np.frombuffer(k_bytes, dtype=np.float64).reshape(3, 3)
+    return torch.from_numpy(np.linalg.inv(K).reshape(9).copy()).to(torch.device("cuda", dev_index))
+
+
 def depth_extents(depth: torch.Tensor, K, view_idx=None):
     """(n,8) fp64: xmin,xmax,ymin,ymax,sum_x,sum_y,sum_z,count of K^-1 [u v 1]^T d over non-zero points."""
     B, res, _ = depth.shape
     dev = depth.device
-    kinv = torch.from_numpy(np.linalg.inv(np.asarray(K, dtype=np.float64))).to(torch.float64).reshape(9).to(dev)
+    kinv = _kinv_device(np.ascontiguousarray(K, dtype=np.float64).tobytes(), dev.index)
     if view_idx is not None:
         view_idx = view_idx.to(torch.int32).contiguous()
         n = view_idx.numel()

@@ -33,11 +33,27 @@ def rle_to_mask(rle: dict) -> np.ndarray:
     return flat.reshape(w, h).T
 
 
+_unit_tables = {}
+
+
+def _unit_table(dev: torch.device) -> torch.Tensor:
+    key = str(dev)
+    if key not in _unit_tables:
+        _unit_tables[key] = (torch.arange(256, dtype=torch.uint8).float() / 255).to(dev)
+    return _unit_tables[key]
+
+
 class Proposals:
     def __init__(self, image, detections_output, target_size=350, scene_id=None, frame_id=None, bbox_extend=0.2,
                  mask_rgb=True, device="cuda"):
         dev = torch.device(device)
-        self.image = (torch.as_tensor(image).float() / 255).permute(2, 0, 1).to(dev)
+        img = torch.as_tensor(image)
+        if img.dtype == torch.uint8:
+            # the frame travels as bytes (a quarter of the fp32 H2D copy) and `.float() / 255` becomes a 256-entry table
+            # filled by the very same host expression, so the values are the reference's bit for bit
+            self.image = _unit_table(dev)[img.to(dev, non_blocking=True).long()].permute(2, 0, 1)
+        else:
+            self.image = (img.float() / 255).permute(2, 0, 1).to(dev)
         self.masks = torch.as_tensor(detections_output["masks"]).bool().to(dev)
         self.boxes = torch.as_tensor(detections_output["boxes"]).int()
         self.rgb_proposal_processor = CropResizePad(target_size=target_size, orig_size=(image.shape[0], image.shape[1]),

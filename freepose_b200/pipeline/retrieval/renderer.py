@@ -45,8 +45,10 @@ class MeshRenderer:
                 self._poses_dev = torch.from_numpy(np.array(self.mesh_poses)).to(self.device, torch.float32)
             return self._poses_dev
         if torch.is_tensor(poses):
-            return poses.to(self.device, torch.float32)
-        return torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device)
+            return poses.to(self.device, torch.float32, non_blocking=True)
+        # (a non-blocking copy from pageable memory is staged by the driver before the call returns: safe for H2D, and
+        # the host does not wait for the work already queued on the stream)
+        return torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device, non_blocking=True)
 
     @on_device
     def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None):

@@ -324,3 +324,34 @@ def test_fine_stage_neighbourhood_matches_reference(golden):
             assert np.array_equal(sel.neighbourhood(T, nb), g[f"close_{i}_{nb}"]), (i, nb)     # pre-filtered path
         np.testing.assert_allclose(d[g[f"close_{i}_15"]], g[f"dist_{i}"], rtol=0, atol=1e-6)
     assert 1234 in g["close_6_5"] and len(g["close_1_5"]) == 0        # a fine pose finds itself; 5 degrees can be empty
+
+
+def test_reciprocal_normalisation_is_exact():
+    """score_rows_kernel evaluates the reference's bf16(t / norm) (F.normalize on a bf16 tensor, pose_estimator.py:85-86)
+    as bf16(fl32(t * fl32(1 / norm))).  t and norm are bf16 values, so the quotient of their 8-bit significands can never
+    come closer than 2^-17 (relative) to a bf16 rounding boundary while the two fp32 roundings err by < 2^-22: both
+    forms round to the same bf16.  All significand pairs, a spread of exponents, plus subnormal-bf16 numerators."""
+    def bf16_round(x):
+        u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        return u.astype(np.uint32).view(np.float32)
+
+    sig = np.arange(128, 256, dtype=np.float32)
+    T, N = np.meshgrid(sig, sig, indexing="ij")
+    for et, en in [(0, 0), (-7, 0), (5, -3), (-20, 6), (12, 12), (-30, -10)]:
+        t = np.ldexp(T, et - 7).astype(np.float32)
+        n = np.ldexp(N, en - 7).astype(np.float32)
+        want = bf16_round((t / n).astype(np.float32))
+        r = (np.float32(1.0) / n).astype(np.float32)
+        got = bf16_round((t * r).astype(np.float32))
+        assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+        # an approximate reciprocal 1 ulp off still rounds the same way (the margin is 2^5 ulps)
+        for off in (-1, 1):
+            r1 = (r.view(np.uint32) + np.uint32(off)).view(np.float32) if off > 0 else (r.view(np.uint32) - np.uint32(1)).view(np.float32)
+            assert np.array_equal(want.view(np.uint32), bf16_round((t * r1).astype(np.float32)).view(np.uint32))
+    # numerators with fewer significant bits (any integer below 256)
+    small = np.arange(1, 128, dtype=np.float32)
+    T, N = np.meshgrid(small, sig, indexing="ij")
+    want = bf16_round((T / N).astype(np.float32))
+    got = bf16_round((T * (np.float32(1.0) / N).astype(np.float32)).astype(np.float32))
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
