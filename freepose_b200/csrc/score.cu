@@ -8,8 +8,9 @@
 //     fine / mask_scores:  score = sum_n(s*w) / sum_n(w) in fp32
 // The kernel reproduces those rounding points and FIXES the fp32 summation order so that the CPU
 // oracle (oracle/score.py, "engine order") can restate it bit-exactly:
-//   * a D-long reduction: lane l accumulates elements c*256 + l*8 + j (c outer, j = 0..7 inner) with
-//     acc = acc + a*b (a*b is exact in fp32 for bf16 inputs), then the xor-butterfly 16,8,4,2,1;
+//   * a D-long reduction: lane l owns elements c*256 + l*8 + j and keeps two running sums, over its even and over its
+//     odd j (c outer), acc = acc + a*b (a*b is exact in fp32 for bf16 inputs); even + odd, then the xor-butterfly
+//     16,8,4,2,1 (rowops.cuh);
 //   * a P-long reduction: lane l accumulates n = l, l+32, ... ascending, then the same butterfly.
 // HBM-bound: every template token row (2 KB) is read exactly once (score_rows_kernel), the per-patch cosines take a
 // second, tiny pass (score_reduce_kernel).
@@ -84,11 +85,13 @@ __host__ __device__ inline size_t exchange_half_floats(int world, int per_rank) 
 // solution (m is odd and m > T), so |t/nrm - boundary| >= boundary / (N * m) > 2^-17 relative, while the reciprocal and
 // the product together err by < 2^-22 (tests/test_oracle_golden.py::test_reciprocal_normalisation_is_exact runs all
 // significand pairs).
+template <int CHUNKS>   // D / 256 at compile time: no per-chunk predicates in the unrolled row loops
 __global__ void __launch_bounds__(ROW_WARPS * 32, 2)
-score_rows_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, int B, int P, int D,
+score_rows_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn, int B, int P,
                   float* __restrict__ patch, unsigned* __restrict__ counter) {
   const int lane = threadIdx.x & 31;
-  const int chunks = D / 256;
+  constexpr int chunks = CHUNKS;
+  constexpr int D = CHUNKS * 256;
   const unsigned total = unsigned((B + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM) * unsigned(P);
   for (;;) {
     unsigned item = 0;
@@ -101,31 +104,32 @@ score_rows_kernel(const bf16* __restrict__ feats_t, const bf16* __restrict__ qn,
 #pragma unroll
     for (int r = 0; r < ROWS_PER_ITEM; ++r)
       if (b0 + r < B) load_row(feats_t + (size_t(b0 + r) * P + n) * D, lane, chunks, t[r]);
-    float qf[MAX_CHUNKS][8];
+    f32x2 qp[MAX_CHUNKS][4];   // the query row as fp32 pairs (even, odd element of every bf16x2 word)
     {
       uint4 qv[MAX_CHUNKS];
       load_row(qn + size_t(n) * D, lane, chunks, qv);
 #pragma unroll
       for (int c = 0; c < MAX_CHUNKS; ++c)
-        if (c < chunks) unpack8(qv[c], qf[c]);
+        if (c < chunks) { qp[c][0] = word2(qv[c].x); qp[c][1] = word2(qv[c].y); qp[c][2] = word2(qv[c].z); qp[c][3] = word2(qv[c].w); }
     }
 #pragma unroll
     for (int r = 0; r < ROWS_PER_ITEM; ++r) {
       if (b0 + r >= B) break;
       const float rnrm = __frcp_rn(row_norm(t[r], chunks));
-      float acc = 0.f;
+      const f32x2 rn2 = pack2(rnrm, rnrm);
+      f32x2 acc2 = pack2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < MAX_CHUNKS; ++c)
         if (c < chunks) {
-          float tf[8];
-          unpack8(t[r][c], tf);
+          const uint32_t w[4] = {t[r][c].x, t[r][c].y, t[r][c].z, t[r][c].w};
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const uint32_t tn = pack_bf16x2(__fmul_rn(tf[j], rnrm), __fmul_rn(tf[j + 1], rnrm));
-            acc = fmaf(bf16lo(tn), qf[c][j], acc);          // == fadd(acc, fmul(tn, q)): the product is exact in fp32
-            acc = fmaf(bf16hi(tn), qf[c][j + 1], acc);
+          for (int i = 0; i < 4; ++i) {
+            float p0, p1;
+            unpack2(mul2(word2(w[i]), rn2), p0, p1);          // t * (1/nrm), both elements of the word in one FMUL2
+            acc2 = fma2(word2(pack_bf16x2(p0, p1)), qp[c][i], acc2);   // bf16(t/nrm) * q: exact products, two running sums
           }
         }
+      float acc = hsum2(acc2);
       acc = warp_sum(acc);
       if (lane == 0) patch[size_t(b0 + r) * P + n] = bf16_round(acc);
     }
@@ -321,7 +325,12 @@ static int score_stages(const bf16* feats_t, const bf16* feat_q, const float* we
   const long long items = (long long)((B + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM) * P;
   const long long want = (items + ROW_WARPS - 1) / ROW_WARPS;
   const int grid = int(want < 2LL * sm_count() ? want : 2LL * sm_count());
-  score_rows_kernel<<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, D, patch, counter);
+  switch (D / 256) {
+    case 1: score_rows_kernel<1><<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, patch, counter); break;
+    case 2: score_rows_kernel<2><<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, patch, counter); break;
+    case 3: score_rows_kernel<3><<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, patch, counter); break;
+    default: score_rows_kernel<4><<<grid, ROW_WARPS * 32, 0, stream>>>(feats_t, qn, B, P, patch, counter); break;
+  }
   FP_CUDA(cudaGetLastError());
   score_reduce_kernel<<<(B + RED_WARPS - 1) / RED_WARPS, RED_WARPS * 32, 0, stream>>>(patch, weights, B, P, scores_out, px);
   FP_CUDA(cudaGetLastError());

@@ -36,15 +36,17 @@ def _bf16_round(x: np.ndarray) -> np.ndarray:
 
 
 def _lane_reduce(prod: np.ndarray) -> np.ndarray:
-    """prod (..., D) fp32 -> (...,) fp32 in kernel order: lane l sums elements c*256 + l*8 + j (c outer, j inner)
-    sequentially, then the xor butterfly 16,8,4,2,1."""
+    """prod (..., D) fp32 -> (...,) fp32 in kernel order (csrc/rowops.cuh): lane l owns elements c*256 + l*8 + j and
+    keeps two running sums -- over its even j and over its odd j, chunks c outer -- adds them (even + odd), then the
+    xor butterfly 16,8,4,2,1 across the 32 lanes."""
     D = prod.shape[-1]
     chunks = D // 256
-    p = prod.reshape(prod.shape[:-1] + (chunks, 32, 8))
-    acc = np.zeros(prod.shape[:-1] + (32,), dtype=np.float32)
+    p = prod.reshape(prod.shape[:-1] + (chunks, 32, 4, 2))
+    acc = np.zeros(prod.shape[:-1] + (32, 2), dtype=np.float32)
     for c in range(chunks):
-        for j in range(8):
-            acc = (acc + p[..., c, :, j]).astype(np.float32)
+        for w in range(4):
+            acc = (acc + p[..., c, :, w, :]).astype(np.float32)
+    acc = (acc[..., 0] + acc[..., 1]).astype(np.float32)
     lanes = np.arange(32)
     for o in (16, 8, 4, 2, 1):
         acc = (acc + acc[..., lanes ^ o]).astype(np.float32)
