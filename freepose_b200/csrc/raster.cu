@@ -68,14 +68,52 @@ __constant__ int c_sample_off[2][4][2] = {
     {{96, 32}, {224, 96}, {32, 160}, {160, 224}},       // msaa 4: (0.375,0.125) (0.875,0.375) (0.125,0.625) (0.625,0.875)
 };
 
+// Screen box of a view: the pixel bounding box of its projected vertices, reduced by the vertex kernel into four
+// zero-initialised words with atomicMax -- {BOX_BIG - min px, BOX_BIG - min py, max px + 1, max py + 1}, 0 = no vertex.
+// Every sample a triangle / point sprite of the view can cover lies inside it, so the general pipeline clears and
+// resolves the 32 bytes per pixel of sample keys only there (a sphere-like object at the benchmark pose covers ~40 % of
+// the image; the rest of the key buffer is neither written nor read).  Views with a vertex that does not project
+// (view_hard) use the whole image: a clipped triangle can cover anything.
+constexpr int BOX_BIG = 1 << 24;
+struct ViewBox { int x0, y0, x1, y1; };   // inclusive, clipped to the image; x0 > x1: empty
+__device__ __forceinline__ ViewBox view_box(const int* __restrict__ boxes, const int* __restrict__ view_hard, int b, int res) {
+  ViewBox vb;
+  if (view_hard[b]) { vb.x0 = 0; vb.y0 = 0; vb.x1 = res - 1; vb.y1 = res - 1; return vb; }
+  const int4 w = reinterpret_cast<const int4*>(boxes)[b];
+  if (w.x == 0) { vb.x0 = 1; vb.y0 = 1; vb.x1 = 0; vb.y1 = 0; return vb; }
+  vb.x0 = max(0, BOX_BIG - w.x - 1); vb.y0 = max(0, BOX_BIG - w.y - 1);     // one pixel of margin (point sprites)
+  vb.x1 = min(res - 1, w.z - BOX_BIG / 2); vb.y1 = min(res - 1, w.w - BOX_BIG / 2);   // (max px + 1: one pixel of margin)
+  return vb;
+}
+
 // `route` (per view, written by the vertex kernel): 1 = general pipeline, 0 = tile pipeline; nullptr = all views general.
+template <int S>
 __global__ void __launch_bounds__(256)
-clear_keys_kernel(unsigned long long* __restrict__ keys, size_t per_view, const int* __restrict__ route) {
+clear_keys_kernel(unsigned long long* __restrict__ keys, int res, const int* __restrict__ route,
+                  const int* __restrict__ boxes, const int* __restrict__ view_hard) {
   const int b = blockIdx.y;
   if (route != nullptr && !route[b]) return;
-  unsigned long long* kv = keys + size_t(b) * per_view;
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < per_view; i += stride) kv[i] = ~0ull;
+  const ViewBox vb = view_box(boxes, view_hard, b, res);
+  if (vb.x0 > vb.x1 || vb.y0 > vb.y1) return;
+  ulonglong2* kv = reinterpret_cast<ulonglong2*>(keys + size_t(b) * res * res * S);   // 16-byte stores
+  constexpr int PER_PIXEL = S == 4 ? 2 : 1;                                           // ulonglong2 per pixel (S = 1: pixel pairs)
+  if (S == 4) {
+    const int bw = (vb.x1 - vb.x0 + 1) * PER_PIXEL, bh = vb.y1 - vb.y0 + 1;
+    const int n = bw * bh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int y = i / bw, x = i - y * bw;
+      kv[(size_t(vb.y0 + y) * res + vb.x0) * PER_PIXEL + x] = make_ulonglong2(~0ull, ~0ull);
+    }
+  } else {
+    // one key per pixel: rows of the box widened to even pixel columns (res is a multiple of 4)
+    const int xa = vb.x0 & ~1, xb = vb.x1 | 1;
+    const int bw = (xb - xa + 1) / 2, bh = vb.y1 - vb.y0 + 1;
+    const int n = bw * bh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int y = i / bw, x = i - y * bw;
+      kv[(size_t(vb.y0 + y) * res + xa) / 2 + x] = make_ulonglong2(~0ull, ~0ull);
+    }
+  }
 }
 
 // camera description shared by the kernels that need camera-space positions again (hard triangles)
@@ -106,10 +144,11 @@ __device__ __forceinline__ void camera_point(const float* __restrict__ verts, co
 __global__ void __launch_bounds__(256)
 vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, ScreenVertex* __restrict__ sv,
               int V, int B, float fx, float fy, float cx, float cy, const float* __restrict__ view_k, float ZNEAR,
-              float ZFAR, int* __restrict__ view_hard) {
+              float ZFAR, int* __restrict__ view_hard, int* __restrict__ boxes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (i >= V) return;
+  int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;   // this vertex's contribution to the view's screen box (0 = none)
+  if (i < V) {
   if (view_k != nullptr) {   // per-view intrinsics (the refiner renders every frame at its own cropped K)
     fx = view_k[4 * b]; fy = view_k[4 * b + 1]; cx = view_k[4 * b + 2]; cy = view_k[4 * b + 3];
   }
@@ -133,8 +172,30 @@ vertex_kernel(const float* __restrict__ verts, const float* __restrict__ poses, 
       o.x = int(uf); o.y = int(vf); o.z = Z; o.iz = __fdiv_rn(1.0f, Z);
     }
   }
-  if (o.x == INT_MIN) view_hard[b] = 1;   // this view has triangles for the homogeneous path (benign race: all write 1)
+  if (o.x == INT_MIN) {
+    view_hard[b] = 1;   // this view has triangles for the homogeneous path (benign race: all write 1)
+  } else {
+    const int px = o.x >> SUB, py = o.y >> SUB;
+    bx0 = BOX_BIG - px; by0 = BOX_BIG - py; bx1 = px + 1 + BOX_BIG / 2; by1 = py + 1 + BOX_BIG / 2;
+  }
   sv[size_t(b) * V + i] = o;
+  }
+  // one atomicMax per CTA and word ("max px + 1" is kept offset by BOX_BIG / 2 so that off-screen negatives stay positive;
+  // per-warp atomics -- 320 per word and view -- cost 130 us of contention at 521 views)
+  __shared__ int s_box[8][4];
+  bx0 = __reduce_max_sync(0xffffffffu, bx0); by0 = __reduce_max_sync(0xffffffffu, by0);
+  bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+  if ((threadIdx.x & 31) == 0) {
+    int* w = s_box[threadIdx.x >> 5];
+    w[0] = bx0; w[1] = by0; w[2] = bx1; w[3] = by1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    int m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = max(m, s_box[w][threadIdx.x]);
+    if (m != 0) atomicMax(&boxes[4 * b + threadIdx.x], m);
+  }
 }
 
 struct TriSetup {
@@ -427,12 +488,15 @@ hard_triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict_
                      int cull) {
   const int b = blockIdx.y;
   if (!view_hard[b]) return;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const ScreenVertex* svb = sv + size_t(b) * V;
   unsigned long long* keys_view = keys + size_t(b) * res * res * S;
   float fx, fy, cx, cy;
   view_intrinsics(cam, b, fx, fy, cx, cy);
+  // (a small grid that loops over the faces: the CTAs of the views that have no such triangle -- all of them at the
+  // benchmark pose -- cost next to nothing to retire)
+  for (int blk = blockIdx.x; blk * int(blockDim.x) < F; blk += gridDim.x) {
+  const int f = blk * blockDim.x + threadIdx.x;
   Hard h;
   h.valid = 0;
   if (f < F) {
@@ -475,6 +539,7 @@ hard_triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict_
         }
       }
     }
+  }
   }
 }
 
@@ -679,10 +744,12 @@ template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* __restrict__ sv,
                const int* __restrict__ faces, const Surface sf, uint8_t* __restrict__ rgb, float* __restrict__ depth,
-               int V, int res, const int* __restrict__ route) {
+               int V, int res, const int* __restrict__ route, const int* __restrict__ boxes,
+               const int* __restrict__ view_hard) {
   const int b = blockIdx.y;
   if (route != nullptr && !route[b]) return;
   const int npix = res * res;
+  const ViewBox vb = view_box(boxes, view_hard, b, res);   // outside: background, the sample keys are not even read
   // (the grid may be smaller than the image: a routed launch keeps it small so that the CTAs of views that are not
   // its business cost nothing to retire)
   for (int blk = blockIdx.x; blk * int(blockDim.x) < npix; blk += gridDim.x) {
@@ -695,7 +762,8 @@ resolve_kernel(const unsigned long long* __restrict__ keys, const ScreenVertex* 
   const ScreenVertex* svb = sv + size_t(b) * V;
   int acc[3] = {0, 0, 0};
   float dep = 0.f;
-  if (live) {
+  if (live && !(px >= vb.x0 && px <= vb.x1 && py >= vb.y0 && py <= vb.y1)) depth[size_t(b) * npix + p] = 0.f;
+  if (live && px >= vb.x0 && px <= vb.x1 && py >= vb.y0 && py <= vb.y1) {
     const unsigned long long* kv = keys + (size_t(b) * npix + p) * S;
     unsigned long long k[S];
     if (S == 4) {
@@ -1034,7 +1102,7 @@ RasterWorkspace raster_layout(int B, int V, int F, int res, int msaa) {
   size_t off = 0;
   w.sv = off;       off += align_up(size_t(B) * V * sizeof(ScreenVertex), 256);
   w.keys = off;     off += align_up(size_t(B) * res * res * msaa * 8, 256);          // general pipeline only
-  w.flags = off;    off += align_up(size_t(B) * sizeof(int), 256);                    // per-view route
+  w.flags = off;    off += align_up(size_t(B) * 5 * sizeof(int) + 16, 256);           // per-view route | per-view screen box (int4)
   w.counters = off; off += align_up((2 * ntiles + size_t(B)) * sizeof(int), 256);     // tile counts | tile cursors | big counts
   w.offsets = off;  off += align_up((ntiles + 1) * sizeof(int), 256);
   w.bins = off;     off += align_up(size_t(B) * size_t(F > 0 ? F : 0) * 4 * sizeof(int), 256);   // <= 4 tiles per binned triangle
@@ -1048,6 +1116,7 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   ScreenVertex* sv = reinterpret_cast<ScreenVertex*>(ws + w.sv);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
   int* view_hard = reinterpret_cast<int*>(ws + w.flags);
+  const int* boxes = reinterpret_cast<const int*>((reinterpret_cast<uintptr_t>(view_hard + a.B) + 15) & ~uintptr_t(15));
   Camera cam;
   cam.verts = a.verts; cam.poses = a.poses; cam.view_k = a.view_k;
   cam.fx = a.fx; cam.fy = a.fy; cam.cx = a.cx; cam.cy = a.cy; cam.znear = znear; cam.zfar = zfar;
@@ -1061,11 +1130,11 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   const dim3 cgrid(unsigned((per_view + 256 * 16 - 1) / (256 * 16)), a.B);
   if (a.primitive == 1) {
     // point clouds: general pipeline for every view
-    clear_keys_kernel<<<cgrid, 256, 0, stream>>>(keys, per_view, nullptr);
+    clear_keys_kernel<S><<<cgrid, 256, 0, stream>>>(keys, a.res, nullptr, boxes, view_hard);
     FP_CUDA(cudaGetLastError());
     point_kernel<S><<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(sv, keys, a.V, a.res, znear, zfar);
     FP_CUDA(cudaGetLastError());
-    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr);
+    resolve_kernel<S, 2><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr, boxes, view_hard);
     FP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1077,18 +1146,18 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   // whose latency its 2-4 resident CTAs per SM hide less well than the 24 warps of triangle_kernel (profiles/r02e_*).
   static const int use_tile = [] { const char* e = getenv("FP_RASTER_TILE"); return e ? atoi(e) : 0; }();
   if (!use_tile) {
-    clear_keys_kernel<<<cgrid, 256, 0, stream>>>(keys, per_view, nullptr);
+    clear_keys_kernel<S><<<cgrid, 256, 0, stream>>>(keys, a.res, nullptr, boxes, view_hard);
     FP_CUDA(cudaGetLastError());
     triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, nullptr);
     FP_CUDA(cudaGetLastError());
-    hard_triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
+    hard_triangle_kernel<S><<<dim3(min(fgrid.x, 16u), a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
     FP_CUDA(cudaGetLastError());
     const dim3 hgrid(min((a.res * a.res + 255) / 256, 24), a.B);
     if (a.texture != nullptr) {
-      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr);
+      resolve_kernel<S, 1><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr, boxes, view_hard);
       resolve_hard_kernel<S, 1><<<hgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
     } else {
-      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr);
+      resolve_kernel<S, 0><<<rgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, nullptr, boxes, view_hard);
       resolve_hard_kernel<S, 0><<<hgrid, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
     }
     FP_CUDA(cudaGetLastError());
@@ -1129,17 +1198,17 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   // ---- general pipeline (views with route == 1: every kernel returns at once for the others; small grids, the kernels
   //      loop, so that those returns cost next to nothing)
   const dim3 rgrid_routed(min((a.res * a.res + 255) / 256, 24), a.B);
-  clear_keys_kernel<<<dim3(min(cgrid.x, 8u), a.B), 256, 0, stream>>>(keys, per_view, view_hard);
+  clear_keys_kernel<S><<<dim3(min(cgrid.x, 8u), a.B), 256, 0, stream>>>(keys, a.res, view_hard, boxes, view_hard);
   FP_CUDA(cudaGetLastError());
   triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, view_hard);
   FP_CUDA(cudaGetLastError());
-  hard_triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
+  hard_triangle_kernel<S><<<dim3(min(fgrid.x, 16u), a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
   FP_CUDA(cudaGetLastError());
   if (a.texture != nullptr) {
-    resolve_kernel<S, 1><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
+    resolve_kernel<S, 1><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard, boxes, view_hard);
     resolve_hard_kernel<S, 1><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
   } else {
-    resolve_kernel<S, 0><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard);
+    resolve_kernel<S, 0><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, a.rgb, a.depth, a.V, a.res, view_hard, boxes, view_hard);
     resolve_hard_kernel<S, 0><<<rgrid_routed, 256, 0, stream>>>(keys, sv, a.faces, sf, cam, view_hard, a.rgb, a.V, a.res);
   }
   FP_CUDA(cudaGetLastError());
@@ -1179,10 +1248,11 @@ int rasterize(const RasterArgs& a, void* workspace, size_t workspace_bytes, cuda
   // algorithmic bytes: RGB u8 + depth f32 out.  Launches: vertex + (points: clear, point, resolve | triangles: 2 bin passes,
   // scan, tile + the general pipeline's clear, triangle, hard triangle, 2 resolves, which return at once for tile views)
   ProfScope prof(PROF_RASTER, double(a.B) * a.res * a.res * 7.0, a.primitive == 1 ? 4 : 10, stream);
-  FP_CUDA(cudaMemsetAsync(view_hard, 0, size_t(a.B) * sizeof(int), stream));
+  int* boxes = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(view_hard + a.B) + 15) & ~uintptr_t(15));   // int4 per view
+  FP_CUDA(cudaMemsetAsync(view_hard, 0, size_t(a.B) * 5 * sizeof(int) + 16, stream));
   const float znear = a.znear > 0.f ? a.znear : ZNEAR_DEFAULT, zfar = a.zfar > 0.f ? a.zfar : ZFAR_DEFAULT;
   vertex_kernel<<<dim3((a.V + 255) / 256, a.B), 256, 0, stream>>>(a.verts, a.poses, sv, a.V, a.B, a.fx, a.fy, a.cx, a.cy,
-                                                                  a.view_k, znear, zfar, view_hard);
+                                                                  a.view_k, znear, zfar, view_hard, boxes);
   FP_CUDA(cudaGetLastError());
   return a.msaa == 4 ? launch_raster<4>(a, ws, w, znear, zfar, stream) : launch_raster<1>(a, ws, w, znear, zfar, stream);
 }
