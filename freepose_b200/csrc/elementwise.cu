@@ -2,6 +2,7 @@
 // stride-14 conv is a pure permutation), special-token broadcast.  All use 16-byte vector accesses.
 #include "common.cuh"
 #include "kernels.h"
+#include "rowops.cuh"
 
 namespace fp {
 
@@ -10,60 +11,86 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over rows of D = 256 * NCH (ViT-L: 1024, ViT-B: 768): one warp per row, NCH x 16-byte loads per lane,
 // fp32 two-pass stats.  Contract (oracle/vit.py contract_layernorm): y = bf16(((x - mean) * rstd) * w + b).
+//
+// HBM-bound on paper (4 KB per row), but inside a step the SM clock sits at the GEMMs' power-capped ~1.3 GHz and the
+// first version's ~380 instructions per row (scalar adds, gamma / beta unpacked again for every row) made it issue-bound
+// there: 4.7-5.0 TB/s in-step against 6.3 TB/s standalone.  Now: persistent warps (two CTAs per SM, rows dealt
+// round-robin) keep gamma and beta unpacked in registers as fp32 pairs, every element-wise step is a packed fp32x2
+// instruction (FADD2 / FFMA2 / FMUL2: the same IEEE operation per lane), the sums run in two independent pair
+// accumulators, and the next row is in flight while the current one is normalised: ~170 instructions per row.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_WARPS = 8;
+using rowops::f32x2;
 
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
                  bf16* __restrict__ out, int rows, float eps, int in_group_stride, int in_skip,
                  int rows_per_group) {
+  using namespace rowops;
   constexpr int LN_D = NCH * 256;
+  constexpr int NP = NCH * 4;   // fp32 pairs per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * LN_WARPS + warp;
+  const int nw = gridDim.x * LN_WARPS;
+  int r = blockIdx.x * LN_WARPS + warp;
   if (r >= rows) return;
-  const int grp = r / rows_per_group;
-  const int idx = r - grp * rows_per_group;
-  const size_t in_row = size_t(grp) * in_group_stride + in_skip + idx;
-  const uint4* xp = reinterpret_cast<const uint4*>(x + in_row * LN_D);
-  float v[NCH * 8];
+  f32x2 w2[NP], b2[NP];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    const uint4 u = xp[c * 32 + lane];
-    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[c * 8 + 2 * j] = bf16lo(uw[j]);
-      v[c * 8 + 2 * j + 1] = bf16hi(uw[j]);
-    }
+    const uint4 wu = __ldg(reinterpret_cast<const uint4*>(w) + c * 32 + lane);
+    const uint4 bu = __ldg(reinterpret_cast<const uint4*>(b) + c * 32 + lane);
+    w2[c * 4 + 0] = word2(wu.x); w2[c * 4 + 1] = word2(wu.y); w2[c * 4 + 2] = word2(wu.z); w2[c * 4 + 3] = word2(wu.w);
+    b2[c * 4 + 0] = word2(bu.x); b2[c * 4 + 1] = word2(bu.y); b2[c * 4 + 2] = word2(bu.z); b2[c * 4 + 3] = word2(bu.w);
   }
-  float s = 0.f;
+  auto row_ptr = [&](int row) {
+    const int grp = row / rows_per_group;
+    const int idx = row - grp * rows_per_group;
+    return reinterpret_cast<const uint4*>(x + (size_t(grp) * in_group_stride + in_skip + idx) * LN_D);
+  };
+  uint4 nxt[NCH];
+  {
+    const uint4* xp = row_ptr(r);
 #pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / LN_D);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) {
-    v[i] -= mean;
-    ss = fmaf(v[i], v[i], ss);
+    for (int c = 0; c < NCH; ++c) nxt[c] = xp[c * 32 + lane];
   }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / LN_D) + eps);
-  const uint4* wp = reinterpret_cast<const uint4*>(w);
-  const uint4* bp = reinterpret_cast<const uint4*>(b);
-  uint4* op = reinterpret_cast<uint4*>(out + size_t(r) * LN_D);
+  for (; r < rows; r += nw) {
+    f32x2 v[NP];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const uint4 wu = __ldg(wp + c * 32 + lane), bu = __ldg(bp + c * 32 + lane);
-    const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
-    const uint32_t bw[4] = {bu.x, bu.y, bu.z, bu.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float y0 = fmaf(v[c * 8 + 2 * j] * rstd, bf16lo(ww[j]), bf16lo(bw[j]));
-      const float y1 = fmaf(v[c * 8 + 2 * j + 1] * rstd, bf16hi(ww[j]), bf16hi(bw[j]));
-      o[j] = pack_bf16x2(y0, y1);
+    for (int c = 0; c < NCH; ++c) {
+      v[c * 4 + 0] = word2(nxt[c].x); v[c * 4 + 1] = word2(nxt[c].y); v[c * 4 + 2] = word2(nxt[c].z); v[c * 4 + 3] = word2(nxt[c].w);
     }
-    op[c * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (r + nw < rows) {
+      const uint4* xp = row_ptr(r + nw);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) nxt[c] = xp[c * 32 + lane];
+    }
+    f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
+#pragma unroll
+    for (int i = 0; i < NP; i += 2) { s0 = add2(s0, v[i]); s1 = add2(s1, v[i + 1]); }
+    const float mean = warp_sum(hsum2(add2(s0, s1))) * (1.0f / LN_D);
+    const f32x2 nmean = pack2(-mean, -mean);
+    f32x2 q0 = pack2(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int i = 0; i < NP; i += 2) {
+      v[i] = add2(v[i], nmean);
+      v[i + 1] = add2(v[i + 1], nmean);
+      q0 = fma2(v[i], v[i], q0);
+      q1 = fma2(v[i + 1], v[i + 1], q1);
+    }
+    const float rstd = rsqrtf(warp_sum(hsum2(add2(q0, q1))) * (1.0f / LN_D) + eps);
+    const f32x2 rstd2 = pack2(rstd, rstd);
+    uint4* op = reinterpret_cast<uint4*>(out + size_t(r) * LN_D);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0, y1;
+        unpack2(fma2(mul2(v[c * 4 + j], rstd2), w2[c * 4 + j], b2[c * 4 + j]), y0, y1);
+        o[j] = pack_bf16x2(y0, y1);
+      }
+      op[c * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -133,7 +160,8 @@ int layernorm_bf16(const bf16* x, const bf16* w, const bf16* b, bf16* out, int r
   FP_REQUIRE(D == 1024 || D == 768, "layernorm: D=%d unsupported (ViT-L: 1024, ViT-B: 768)", D);
   if (rows <= 0) return 0;
   FP_REQUIRE(rows_per_group > 0, "layernorm: rows_per_group must be positive");
-  const int blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int want = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int blocks = want < 2 * sm_count() ? want : 2 * sm_count();
   ProfScope prof(PROF_LAYERNORM, 2.0 * double(rows) * D * 2, 1, stream);
   if (D == 1024)
     layernorm_kernel<4><<<blocks, LN_WARPS * 32, 0, stream>>>(x, w, b, out, rows, eps, in_group_stride, in_skip,
