@@ -247,11 +247,11 @@ __device__ __forceinline__ bool setup_triangle(const ScreenVertex& a0, const Scr
 // 1/z is affine in screen space.
 __device__ __forceinline__ float sample_depth(const TriSetup& t, long long e0, long long e1, long long e2,
                                               const long long* bias) {
-  const float w0 = __fdiv_rn(__ll2float_rn(e0 + bias[0]), t.area);
-  const float w1 = __fdiv_rn(__ll2float_rn(e1 + bias[1]), t.area);
-  const float w2 = __fdiv_rn(__ll2float_rn(e2 + bias[2]), t.area);
-  const float iz = __fadd_rn(__fadd_rn(__fmul_rn(w0, t.iz[0]), __fmul_rn(w1, t.iz[1])), __fmul_rn(w2, t.iz[2]));
-  return __fdiv_rn(1.0f, iz);
+  // z = area / (e0/z0 + e1/z1 + e2/z2): ONE division per sample (the form w_i = e_i / area, z = 1 / sum w_i/z_i costs
+  // four, and the divisions were a quarter of the triangle kernel); oracle/raster_ref.c evaluates the same expression
+  const float f0 = __ll2float_rn(e0 + bias[0]), f1 = __ll2float_rn(e1 + bias[1]), f2 = __ll2float_rn(e2 + bias[2]);
+  const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, t.iz[0]), __fmul_rn(f1, t.iz[1])), __fmul_rn(f2, t.iz[2]));
+  return __fdiv_rn(t.area, den);
 }
 
 template <int S>
@@ -281,7 +281,7 @@ template <int S>
 __global__ void __launch_bounds__(256, 3)   // 80 registers: 3 CTAs / SM hide more latency than the 44 spilled bytes cost (-9 %)
 triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ faces,
                 unsigned long long* __restrict__ keys, int V, int F, int res, int cull, float ZNEAR, float ZFAR,
-                const int* __restrict__ route) {
+                const int* __restrict__ route, int big_pixels) {
   const int b = blockIdx.y;
   if (route != nullptr && !route[b]) return;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,7 +303,7 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   }
   const int w = t.valid ? (t.xmax - t.xmin + 1) : 0;
   const int h = t.valid ? (t.ymax - t.ymin + 1) : 0;
-  const bool big = w * h > BIG_TRI_PIXELS;
+  const bool big = w * h > big_pixels;
   if (t.valid && !big && !t.fits32) {
     // small on screen but long off screen (clipped by the viewport): 64-bit evaluation per sample
     for (int py = t.ymin; py <= t.ymax; ++py)
@@ -333,11 +333,9 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
           const int e1 = a[1] * dx + b[1] * dy + c[1];
           const int e2 = a[2] * dx + b[2] * dy + c[2];
           if ((e0 | e1 | e2) >= 0) {
-            const float w0 = __fdiv_rn(__int2float_rn(e0 + bi[0]), t.area);
-            const float w1 = __fdiv_rn(__int2float_rn(e1 + bi[1]), t.area);
-            const float w2 = __fdiv_rn(__int2float_rn(e2 + bi[2]), t.area);
-            const float iz = __fadd_rn(__fadd_rn(__fmul_rn(w0, t.iz[0]), __fmul_rn(w1, t.iz[1])), __fmul_rn(w2, t.iz[2]));
-            const float z = __fdiv_rn(1.0f, iz);
+            const float f0 = __int2float_rn(e0 + bi[0]), f1 = __int2float_rn(e1 + bi[1]), f2 = __int2float_rn(e2 + bi[2]);
+            const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, t.iz[0]), __fmul_rn(f1, t.iz[1])), __fmul_rn(f2, t.iz[2]));
+            const float z = __fdiv_rn(t.area, den);   // (sample_depth's expression)
             if (z > ZNEAR && z < ZFAR)
               atomicMin(&keys_view[(size_t(py) * res + px) * S + s],
                         ((unsigned long long)__float_as_uint(z) << 32) | unsigned(f));
@@ -666,19 +664,20 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   }
   long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
   if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
-  const float fa = __ll2float_rn(area);
   // perspective weights at (sx, sy) (unbiased edge values: the point may lie outside the triangle)
   auto weights = [&](long long sx, long long sy, float& w0, float& w1, float& w2, float& wsum) {
     const long long e0 = (long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x);
     const long long e1 = (long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x);
     const long long e2 = (long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x);
-    w0 = __fmul_rn(__fdiv_rn(__ll2float_rn(e0), fa), v0.iz);
-    w1 = __fmul_rn(__fdiv_rn(__ll2float_rn(e1), fa), v1.iz);
-    w2 = __fmul_rn(__fdiv_rn(__ll2float_rn(e2), fa), v2.iz);
-    wsum = __fadd_rn(__fadd_rn(w0, w1), w2);
+    // w_i = e_i / z_i (the common factor 1 / area cancels in the ratio below); `wsum` returns 1 / sum w_i: ONE division
+    // per evaluation point instead of three for the weights and one per interpolated attribute
+    w0 = __fmul_rn(__ll2float_rn(e0), v0.iz);
+    w1 = __fmul_rn(__ll2float_rn(e1), v1.iz);
+    w2 = __fmul_rn(__ll2float_rn(e2), v2.iz);
+    wsum = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(w0, w1), w2));
   };
-  auto interp = [&](float w0, float w1, float w2, float wsum, float a0, float a1, float a2) {
-    return __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, a0), __fmul_rn(w1, a1)), __fmul_rn(w2, a2)), wsum);
+  auto interp = [&](float w0, float w1, float w2, float rsum, float a0, float a1, float a2) {
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, a0), __fmul_rn(w1, a1)), __fmul_rn(w2, a2)), rsum);
   };
   const long long sx = ((long long)px << SUB) + 128, sy = ((long long)py << SUB) + 128;
   float w0, w1, w2, wsum;
@@ -964,11 +963,9 @@ __device__ __forceinline__ void raster_box(const TriSetup& t, const long long* b
           const int e1 = a[1] * dx + b[1] * dy + c[1];
           const int e2 = a[2] * dx + b[2] * dy + c[2];
           if ((e0 | e1 | e2) >= 0) {
-            const float w0 = __fdiv_rn(__int2float_rn(e0 + bi[0]), t.area);
-            const float w1 = __fdiv_rn(__int2float_rn(e1 + bi[1]), t.area);
-            const float w2 = __fdiv_rn(__int2float_rn(e2 + bi[2]), t.area);
-            const float iz = __fadd_rn(__fadd_rn(__fmul_rn(w0, t.iz[0]), __fmul_rn(w1, t.iz[1])), __fmul_rn(w2, t.iz[2]));
-            const float z = __fdiv_rn(1.0f, iz);
+            const float f0 = __int2float_rn(e0 + bi[0]), f1 = __int2float_rn(e1 + bi[1]), f2 = __int2float_rn(e2 + bi[2]);
+            const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, t.iz[0]), __fmul_rn(f1, t.iz[1])), __fmul_rn(f2, t.iz[2]));
+            const float z = __fdiv_rn(t.area, den);   // (sample_depth's expression)
             if (z > ZNEAR && z < ZFAR) atomicMin(&slot[s], ((unsigned long long)__float_as_uint(z) << 32) | face);
           }
         }
@@ -1145,10 +1142,11 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   // interpolation), which the tile pipeline runs three times (two binning passes + the tile kernel) instead of once, and
   // whose latency its 2-4 resident CTAs per SM hide less well than the 24 warps of triangle_kernel (profiles/r02e_*).
   static const int use_tile = [] { const char* e = getenv("FP_RASTER_TILE"); return e ? atoi(e) : 0; }();
+  static const int big_pixels = [] { const char* e = getenv("FP_RASTER_BIG"); return e ? atoi(e) : BIG_TRI_PIXELS; }();   // perf experiments
   if (!use_tile) {
     clear_keys_kernel<S><<<cgrid, 256, 0, stream>>>(keys, a.res, nullptr, boxes, view_hard);
     FP_CUDA(cudaGetLastError());
-    triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, nullptr);
+    triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, nullptr, big_pixels);
     FP_CUDA(cudaGetLastError());
     hard_triangle_kernel<S><<<dim3(min(fgrid.x, 16u), a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
     FP_CUDA(cudaGetLastError());
@@ -1200,7 +1198,7 @@ int launch_raster(const RasterArgs& a, uint8_t* ws, const RasterWorkspace& w, fl
   const dim3 rgrid_routed(min((a.res * a.res + 255) / 256, 24), a.B);
   clear_keys_kernel<S><<<dim3(min(cgrid.x, 8u), a.B), 256, 0, stream>>>(keys, a.res, view_hard, boxes, view_hard);
   FP_CUDA(cudaGetLastError());
-  triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, view_hard);
+  triangle_kernel<S><<<fgrid, 256, 0, stream>>>(sv, a.faces, keys, a.V, a.F, a.res, a.cull_backfaces, znear, zfar, view_hard, big_pixels);
   FP_CUDA(cudaGetLastError());
   hard_triangle_kernel<S><<<dim3(min(fgrid.x, 16u), a.B), 256, 0, stream>>>(sv, a.faces, cam, view_hard, keys, a.V, a.F, a.res, a.cull_backfaces);
   FP_CUDA(cudaGetLastError());

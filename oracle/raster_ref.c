@@ -113,11 +113,13 @@ static Weights persp_weights(SV v0, SV v1, SV v2, float fa, int64_t sx, int64_t 
   int64_t e1 = (int64_t)(v0.x - v2.x) * (sy - v2.y) - (int64_t)(v0.y - v2.y) * (sx - v2.x);
   int64_t e2 = (int64_t)(v1.x - v0.x) * (sy - v0.y) - (int64_t)(v1.y - v0.y) * (sx - v0.x);
   Weights w;
-  w.w0 = ((float)e0 / fa) * v0.iz; w.w1 = ((float)e1 / fa) * v1.iz; w.w2 = ((float)e2 / fa) * v2.iz;
-  w.wsum = (w.w0 + w.w1) + w.w2;
+  /* w_i = e_i / z_i (1 / area cancels in the ratio); wsum holds 1 / sum w_i */
+  (void)fa;
+  w.w0 = (float)e0 * v0.iz; w.w1 = (float)e1 * v1.iz; w.w2 = (float)e2 * v2.iz;
+  w.wsum = 1.0f / ((w.w0 + w.w1) + w.w2);
   return w;
 }
-static float interp(Weights w, float a0, float a1, float a2) { return ((w.w0 * a0 + w.w1 * a1) + w.w2 * a2) / w.wsum; }
+static float interp(Weights w, float a0, float a1, float a2) { return ((w.w0 * a0 + w.w1 * a1) + w.w2 * a2) * w.wsum; }
 
 /* ---- hard triangles: homogeneous rasterisation ------------------------------------------------------------------ */
 typedef struct { float n0[3], n1[3], n2[3]; float adet, sgn; int xlo, xhi, ylo, yhi; int valid; } Hard;
@@ -329,9 +331,9 @@ static void render_view(const float* verts, const int32_t* faces, const Surface*
             if (e[i] < 0 || (e[i] == 0 && !topleft)) inside = 0;
           }
           if (!inside) continue;
-          float w0 = (float)e[0] / farea, w1 = (float)e[1] / farea, w2 = (float)e[2] / farea;
-          float izs = (w0 * iz[0] + w1 * iz[1]) + w2 * iz[2];
-          float z = 1.0f / izs;
+          /* perspective-correct depth: 1/z is affine in screen space, z = area / (e0/z0 + e1/z1 + e2/z2) */
+          float den = ((float)e[0] * iz[0] + (float)e[1] * iz[1]) + (float)e[2] * iz[2];
+          float z = farea / den;
           if (!(z > ZNEAR && z < ZFAR)) continue;
           size_t k = ((size_t)py * res + px) * S + s;
           /* GL_LESS with primitives in order: strictly nearer wins; on equal depth the earlier face stays */
