@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "rowops.cuh"
+#include "ln_row.cuh"
 
 namespace fp {
 
@@ -64,31 +65,13 @@ layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const b
 #pragma unroll
       for (int c = 0; c < NCH; ++c) nxt[c] = xp[c * 32 + lane];
     }
-    f32x2 s0 = pack2(0.f, 0.f), s1 = s0;
-#pragma unroll
-    for (int i = 0; i < NP; i += 2) { s0 = add2(s0, v[i]); s1 = add2(s1, v[i + 1]); }
-    const float mean = warp_sum(hsum2(add2(s0, s1))) * (1.0f / LN_D);
-    const f32x2 nmean = pack2(-mean, -mean);
-    f32x2 q0 = pack2(0.f, 0.f), q1 = q0;
-#pragma unroll
-    for (int i = 0; i < NP; i += 2) {
-      v[i] = add2(v[i], nmean);
-      v[i + 1] = add2(v[i + 1], nmean);
-      q0 = fma2(v[i], v[i], q0);
-      q1 = fma2(v[i + 1], v[i + 1], q1);
-    }
-    const float rstd = rsqrtf(warp_sum(hsum2(add2(q0, q1))) * (1.0f / LN_D) + eps);
-    const f32x2 rstd2 = pack2(rstd, rstd);
+    lnrow::normalise_pairs<NP>(v, 1.0f / LN_D, eps);   // (x - mean) * rstd
     uint4* op = reinterpret_cast<uint4*>(out + size_t(r) * LN_D);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       uint32_t o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float y0, y1;
-        unpack2(fma2(mul2(v[c * 4 + j], rstd2), w2[c * 4 + j], b2[c * 4 + j]), y0, y1);
-        o[j] = pack_bf16x2(y0, y1);
-      }
+      for (int j = 0; j < 4; ++j) o[j] = lnrow::affine_word(v[c * 4 + j], w2[c * 4 + j], b2[c * 4 + j]);
       op[c * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ln_row.cuh"
 
 namespace fp {
 
@@ -51,6 +52,13 @@ struct Params {
   int tokens_per_img;
   int token_offset;
   int debug;  // perf experiments only: 1 = skip epilogue stores, 2 = always load tile (0,0)
+  // fused LayerNorm of the output rows (gemm2_kernel<EPI_BIAS_LS_RES, true>)
+  const bf16* ln_w;
+  const bf16* ln_b;
+  bf16* ln_out;
+  float ln_eps;
+  unsigned* ln_counters;   // one word per 128 output rows: arrivals of the epilogue warps that stored a tile of them
+  unsigned ln_expect;      // epoch * (epilogue warps * N tiles)
 };
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2: two fp32 lanes per issue slot) -------------------
@@ -380,6 +388,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm fused into the residual GEMMs (attn.proj / mlp.fc2 -> norm2 / next block's norm1).
+// The GEMM's tiles own 256 of the 1024 columns of a row, so the normalisation cannot happen in a tile's epilogue.  Instead
+// the kernel carries one extra warpgroup: every epilogue warp, once the bulk stores of its part of a tile have completed,
+// adds 1 to the counter of its 128-row block; the LayerNorm warps (4 per CTA, 592 on the chip) take units of 8 rows
+// round-robin, wait until the block's counter says that all N tiles of those rows are in memory, read the rows back --
+// from L2, they were written microseconds ago -- and write the normalised rows.  The standalone LayerNorm launch (557 MB
+// through HBM, 0.1 ms, 44 times per step) disappears: the read hits L2 and the write overlaps the GEMM's tensor work.
+// The arithmetic is lnrow::normalise_pairs / affine_word, the same code as layernorm_kernel: identical bits.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_WARPS_PER_CTA = 4;
+constexpr int LN_UNIT_ROWS = 8;
+constexpr int LN_AHEAD = 3;                   // rows in flight per LayerNorm warp
+constexpr int LN_SMEM_BYTES = 2 * 1024 * 2;   // gamma | beta as bf16, D <= 1024
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NCH>
+__device__ __forceinline__ void layernorm_warps(const Params& p, uint8_t* ln_smem, int lw, int lane) {
+  using namespace rowops;
+  constexpr int D = NCH * 256, NP = NCH * 4;
+  // gamma / beta -> shared memory (the four LayerNorm warps of this CTA only: named barrier 1)
+  uint4* sgb = reinterpret_cast<uint4*>(ln_smem);
+  for (int i = lw * 32 + lane; i < 2 * NCH * 32; i += LN_WARPS_PER_CTA * 32)
+    sgb[i] = __ldg(reinterpret_cast<const uint4*>(i < NCH * 32 ? p.ln_w : p.ln_b) + (i < NCH * 32 ? i : i - NCH * 32));
+  asm volatile("bar.sync 1, %0;" ::"n"(LN_WARPS_PER_CTA * 32) : "memory");
+  if (p.debug & 4) return;   // perf experiments: no LayerNorm work at all (WRONG results)
+  const long long units = ((long long)p.M + LN_UNIT_ROWS - 1) / LN_UNIT_ROWS;
+  const long long stride = (long long)gridDim.x * LN_WARPS_PER_CTA;
+  for (long long u = (long long)blockIdx.x * LN_WARPS_PER_CTA + lw; u < units; u += stride) {
+    const int row0 = int(u) * LN_UNIT_ROWS;
+    const int row1 = min(row0 + LN_UNIT_ROWS, p.M);
+    if (lane == 0) {
+      const unsigned* c = p.ln_counters + (row0 >> 7);
+      unsigned spins = 0;
+      while (ld_acquire_gpu(c) < p.ln_expect) {
+        __nanosleep(64);
+        if (++spins > (1u << 26)) __trap();   // a protocol bug must not hang the device
+      }
+    }
+    __syncwarp();
+    // rows come back from L2 (ld.cg: no L1, which may still hold the residual values this SM read before the update);
+    // LN_AHEAD rows are in flight per warp: a row costs ~1 us of L2 latency under the GEMM's own traffic, and a warp owes
+    // M / 592 rows per launch -- one row at a time made these warps the kernel's critical path
+    uint4 ring[LN_AHEAD][NCH];
+#pragma unroll
+    for (int k = 0; k < LN_AHEAD; ++k)
+      if (row0 + k < row1) {
+        const uint4* xp = reinterpret_cast<const uint4*>(p.out + size_t(row0 + k) * p.ldo);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) ring[k][c] = __ldcg(xp + c * 32 + lane);
+      }
+#pragma unroll
+    for (int k = 0; k < LN_UNIT_ROWS; ++k) {
+      const int r = row0 + k;
+      if (r >= row1) break;
+      f32x2 v[NP];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint4 u = ring[k % LN_AHEAD][c];
+        v[c * 4 + 0] = word2(u.x); v[c * 4 + 1] = word2(u.y); v[c * 4 + 2] = word2(u.z); v[c * 4 + 3] = word2(u.w);
+      }
+      if (r + LN_AHEAD < row1) {
+        const uint4* xp = reinterpret_cast<const uint4*>(p.out + size_t(r + LN_AHEAD) * p.ldo);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) ring[k % LN_AHEAD][c] = __ldcg(xp + c * 32 + lane);
+      }
+      lnrow::normalise_pairs<NP>(v, 1.0f / D, p.ln_eps);
+      uint4* op = reinterpret_cast<uint4*>(p.ln_out + size_t(r) * D);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint4 wu = sgb[c * 32 + lane], bu = sgb[NCH * 32 + c * 32 + lane];
+        uint4 o;
+        o.x = lnrow::affine_word(v[c * 4 + 0], word2(wu.x), word2(bu.x));
+        o.y = lnrow::affine_word(v[c * 4 + 1], word2(wu.y), word2(bu.y));
+        o.z = lnrow::affine_word(v[c * 4 + 2], word2(wu.z), word2(bu.z));
+        o.w = lnrow::affine_word(v[c * 4 + 3], word2(wu.w), word2(bu.w));
+        op[c * 32 + lane] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2-CTA variant (cta_group::2): the two CTAs of a cluster drive ONE 256 x 256 tcgen05.mma.  Each CTA stages its own
 // 128 rows of A and 128 of the 256 W rows per K slab (32 KB/stage instead of 48 KB: 6 stages, and half the operand
 // traffic per SM), the leader CTA issues the MMAs, each CTA drains the 128 accumulator rows that live in its own
@@ -389,9 +487,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = 2 * BM * BK * 2;  // A half (16 KB) + W half (16 KB)
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + OUT_STAGE_OFF + OUT_STAGE_BYTES;
+constexpr int NUM_THREADS_LN = NUM_THREADS + LN_WARPS_PER_CTA * 32;   // + the LayerNorm warpgroup (LN = true)
+constexpr int UTIL_REGS = 40, LN_REGS = 96 + (96 - UTIL_REGS);        // setmaxnreg: 4 x 40 + 12 x 96 + 4 x 152 warps = 640 x 96
 
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+template <int MODE, bool LN = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LN ? NUM_THREADS_LN : NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -437,6 +537,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp < 4) {
+  // (LN: 640 threads x 96 registers at launch; the four utility warps need 40, the LayerNorm warpgroup takes what they
+  // free.  Each setmaxnreg sits at the top of its warpgroup's own branch, which is what lets ptxas allocate the code it
+  // dominates within the new limit.)
+  if (LN) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(UTIL_REGS));
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
@@ -486,7 +591,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else if (LN && warp >= 4 + NUM_EPI_WARPS) {
+    // ------------------------------------------------------------------ LayerNorm of finished rows (see above)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LN_REGS));   // the registers warps 0..3 gave up
+    uint8_t* ln_smem = smem + STAGES2 * STAGE2_BYTES + OUT_STAGE_OFF + OUT_STAGE_BYTES;
+    if (p.N == 1024) layernorm_warps<4>(p, ln_smem, warp - 4 - NUM_EPI_WARPS, lane);
+    else             layernorm_warps<3>(p, ln_smem, warp - 4 - NUM_EPI_WARPS, lane);
+  } else {
     // ------------------------------------------------------------------ epilogue (each CTA drains its 128 rows)
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
@@ -506,10 +618,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (LN && !(p.debug & 8)) {   // (8: perf experiments, no completion signalling -- with 4)
+        // this warp's part of the tile is in memory (bulk stores complete) -> one arrival on the 128-row block's counter
+        tma_store_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");   // the async-proxy writes before the generic-proxy release below
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          red_release_gpu_add(p.ln_counters + (m_blk * 2 + int(rank)), 1u);
+        }
+      }
     }
   }
 
-  if (warp >= 4) tma_store_wait_all();
+  if (warp >= 4 && warp < 4 + NUM_EPI_WARPS) tma_store_wait_all();
   tc_fence_before();
   cluster_sync_all();  // the peer may still be signalling barriers / reading operands that live in this CTA
   if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
@@ -534,6 +656,18 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   return 0;
 }
 
+int launch2_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
+               cudaStream_t stream) {
+  auto kern = gemm2_kernel<EPI_BIAS_LS_RES, true>;
+  FP_ENSURE_DYN_SMEM(kern, SMEM2_BYTES + LN_SMEM_BYTES);
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
+  const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  ProfScope prof(prof_kind(EPI_BIAS_LS_RES, p.K), 2.0 * double(p.M) * double(p.N) * double(p.K), 1, stream);
+  kern<<<2 * clusters, NUM_THREADS_LN, SMEM2_BYTES + LN_SMEM_BYTES, stream>>>(tmA, tmB, tmOut, p);
+  FP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int MODE>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const Params& p,
             cudaStream_t stream) {
@@ -548,6 +682,13 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
 
 }  // namespace
 
+static bool two_cta_path(int M) {
+  static const int force = [] { const char* e = getenv("FP_GEMM_CTAS"); return e ? atoi(e) : 0; }();
+  return force ? force == 2 : M >= 2048;
+}
+
+bool gemm_fuses_layernorm(int M, int N) { return two_cta_path(M) && (N == 1024 || N == 768); }
+
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   FP_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   FP_REQUIRE(a.N % BN == 0, "gemm: N=%d must be a multiple of %d", a.N, BN);
@@ -555,8 +696,14 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   FP_REQUIRE(a.A && a.W && a.out && a.bias, "gemm: null operand");
   FP_REQUIRE(a.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
   // large problems: 2-CTA clusters (256 x 256 tiles); small ones (e.g. the single query crop): 1-CTA 128 x 256 tiles
-  static const int force = [] { const char* e = getenv("FP_GEMM_CTAS"); return e ? atoi(e) : 0; }();
-  const bool two = force ? force == 2 : a.M >= 2048;
+  const bool two = two_cta_path(a.M);
+  const bool fuse_ln = a.ln_out != nullptr;
+  if (fuse_ln) {
+    FP_REQUIRE(a.mode == EPI_BIAS_LS_RES && gemm_fuses_layernorm(a.M, a.N) && a.ldo == a.N,
+               "gemm: fused LayerNorm needs the residual epilogue, M >= 2048, N = ldo = 1024 or 768");
+    FP_REQUIRE(a.ln_w && a.ln_b && a.ln_counters && a.ln_epoch > 0, "gemm: fused LayerNorm needs weights, counters and an epoch");
+    FP_REQUIRE(a.ln_out != a.out && a.ln_out != a.A, "gemm: the fused LayerNorm output must not alias the GEMM's operands");
+  }
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_2d_bf16(&tmA, a.A, uint64_t(a.M), uint64_t(a.K), uint64_t(a.lda), BM, BK)) return rc;
   if (int rc = make_tmap_2d_bf16(&tmB, a.W, uint64_t(a.N), uint64_t(a.K), uint64_t(a.K), two ? BN / 2 : BN, BK)) return rc;
@@ -575,6 +722,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.token_offset = a.token_offset;
   static const int dbg = [] { const char* e = getenv("FP_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
+  p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_eps = a.ln_eps; p.ln_counters = a.ln_counters;
+  p.ln_expect = a.ln_epoch * unsigned(NUM_EPI_WARPS * (a.N / BN));
+  if (fuse_ln) return launch2_ln(tmA, tmB, tmOut, p, stream);
   switch (a.mode) {
     case EPI_BIAS: return two ? launch2<EPI_BIAS>(tmA, tmB, tmOut, p, stream) : launch<EPI_BIAS>(tmA, tmB, tmOut, p, stream);
     case EPI_BIAS_GELU:

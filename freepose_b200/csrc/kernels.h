@@ -31,8 +31,18 @@ struct GemmArgs {
   const bf16* gamma;  // [N]             (EPI_BIAS_LS_RES)
   const bf16* res;    // [M, ldo] residual (EPI_BIAS_LS_RES, may alias out) | pos-embed [1+P, N] (EPI_PATCH_EMBED)
   int patches_per_img, tokens_per_img, token_offset;  // EPI_PATCH_EMBED row remap
+  // EPI_BIAS_LS_RES only, optional (ln_out != nullptr): LayerNorm of the finished rows of `out` by extra warps of the
+  // same kernel -> ln_out [M, N].  ln_counters: ceil(M / 128) words, zeroed once by the caller and shared by consecutive
+  // fused launches; ln_epoch = 1, 2, ... counts those launches (the kernel expects counter >= epoch * arrivals).
+  const bf16* ln_w = nullptr;
+  const bf16* ln_b = nullptr;
+  bf16* ln_out = nullptr;
+  float ln_eps = 0.f;
+  unsigned* ln_counters = nullptr;
+  unsigned ln_epoch = 0;
 };
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+bool gemm_fuses_layernorm(int M, int N);   // whether gemm_bf16 accepts ln_out for this problem (large M, N = 1024 | 768)
 
 // ---------------------------------------------------------------------------------------- attention
 // qkv: [B*T, 3*H*64] bf16 (q | k | v, head-major inside each), out: [B*T, H*64] bf16.

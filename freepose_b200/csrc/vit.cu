@@ -1,6 +1,8 @@
 // DINOv2 ViT-L/14-reg (or ViT-B/14-reg: dim 768, 12 heads, MLP 3072) forward to layer L + final norm (reference src/pipeline/retrieval/dino.py:14-32):
 // sequencing of the kernels over caller-provided workspace.  Stateless: weights and buffers are borrowed
 // device pointers (include/freepose_b200.h: fp_vit_weights / fp_vit_forward).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "freepose_b200.h"
@@ -16,7 +18,8 @@ size_t vit_workspace_bytes(int dim, int mlp_dim, int B, int res) {
   const size_t D = dim > 0 ? dim : 1024, MLP = mlp_dim > 0 ? mlp_dim : 4096;
   const int g = res / 14, P = g * g, T = P + 1 + NREG;
   const size_t M = size_t(B) * T;
-  return align256(M * D * 2) * 2        // residual stream x, scratch h
+  return align256(M * D * 2) * 3        // residual stream x, scratch h (LN1 out / attention out), h2 (LN2 out)
+         + align256((M / 128 + 2) * 4)  // fused-LayerNorm row-block counters
          + align256(M * 3 * D * 2)      // qkv
          + align256(M * MLP * 2)        // mlp hidden
          + align256(size_t(B) * P * KPAD * 2)  // patch matrix
@@ -45,6 +48,8 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   bf16* x = reinterpret_cast<bf16*>(ws); ws += align256(M * size_t(D) * 2);
   bf16* h = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
+  bf16* h2 = reinterpret_cast<bf16*>(ws); ws += align256(M * D * 2);
+  unsigned* ln_counters = reinterpret_cast<unsigned*>(ws); ws += align256((M / 128 + 2) * 4);
   bf16* qkv = reinterpret_cast<bf16*>(ws); ws += align256(M * 3 * D * 2);
   bf16* mlp = reinterpret_cast<bf16*>(ws); ws += align256(M * MLP * 2);
   bf16* patches = reinterpret_cast<bf16*>(ws);
@@ -69,11 +74,21 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
   }
 
   // ---- transformer blocks
+  // norm2 and the NEXT block's norm1 CAN run inside the residual GEMMs that produce their input (gemm.cu: layernorm_warps)
+  // when the batch is large enough for the 2-CTA kernels.  FP_FUSE_LN: bit 0 = norm1 of the next block inside fc2, bit 1 =
+  // norm2 inside proj.  Bit-identical tokens either way; OFF by default: measured neutral (DESIGN.md section 6 -- under
+  // the power cap the LayerNorm work costs the GEMM as much time inside the kernel as its own launch costs outside).
+  const char* fuse_env = getenv("FP_FUSE_LN");
+  const int fuse_mask = gemm_fuses_layernorm(int(M), D) ? (fuse_env ? atoi(fuse_env) : 0) : 0;
+  const bool fuse_fc2 = (fuse_mask & 1) != 0, fuse_proj = (fuse_mask & 2) != 0;
+  unsigned ln_epoch = 0;
+  if (fuse_mask && layer > 0) FP_CUDA(cudaMemsetAsync(ln_counters, 0, (M / 128 + 2) * 4, stream));
   const float scale = 0.125f;  // head_dim^-0.5
   for (int l = 0; l < layer; ++l) {
     const fp_vit_layer& L = w->layers[l];
     auto P16 = [](const void* p) { return reinterpret_cast<const bf16*>(p); };
-    if (int rc = layernorm_bf16(x, P16(L.ln1_w), P16(L.ln1_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
+    if (!fuse_fc2 || l == 0)   // (with fusion the previous block's fc2 has already written norm1(x) into h)
+      if (int rc = layernorm_bf16(x, P16(L.ln1_w), P16(L.ln1_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
     GemmArgs a{};
     a.A = h; a.lda = D; a.W = P16(L.qkv_w); a.out = qkv; a.ldo = 3 * D; a.M = int(M); a.N = 3 * D; a.K = D;
     a.mode = EPI_BIAS; a.bias = P16(L.qkv_b);
@@ -82,15 +97,25 @@ int vit_forward(const fp_vit_weights* w, const void* input, int input_kind, int 
     a = GemmArgs{};
     a.A = h; a.lda = D; a.W = P16(L.proj_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = D;
     a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.proj_b); a.gamma = P16(L.ls1); a.res = x;
+    if (fuse_proj) {   // norm2 -> h2 (h holds the attention output this GEMM is reading)
+      a.ln_w = P16(L.ln2_w); a.ln_b = P16(L.ln2_b); a.ln_out = h2; a.ln_eps = 1e-6f;
+      a.ln_counters = ln_counters; a.ln_epoch = ++ln_epoch;
+    }
     if (int rc = gemm_bf16(a, stream)) return rc;
-    if (int rc = layernorm_bf16(x, P16(L.ln2_w), P16(L.ln2_b), h, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
+    if (!fuse_proj)
+      if (int rc = layernorm_bf16(x, P16(L.ln2_w), P16(L.ln2_b), h2, int(M), D, 1e-6f, int(M), 0, int(M), stream)) return rc;
     a = GemmArgs{};
-    a.A = h; a.lda = D; a.W = P16(L.fc1_w); a.out = mlp; a.ldo = MLP; a.M = int(M); a.N = MLP; a.K = D;
+    a.A = h2; a.lda = D; a.W = P16(L.fc1_w); a.out = mlp; a.ldo = MLP; a.M = int(M); a.N = MLP; a.K = D;
     a.mode = EPI_BIAS_GELU; a.bias = P16(L.fc1_b);
     if (int rc = gemm_bf16(a, stream)) return rc;
     a = GemmArgs{};
     a.A = mlp; a.lda = MLP; a.W = P16(L.fc2_w); a.out = x; a.ldo = D; a.M = int(M); a.N = D; a.K = MLP;
     a.mode = EPI_BIAS_LS_RES; a.bias = P16(L.fc2_b); a.gamma = P16(L.ls2); a.res = x;
+    if (fuse_fc2 && l + 1 < layer) {   // the next block's norm1 -> h
+      const fp_vit_layer& Ln = w->layers[l + 1];
+      a.ln_w = P16(Ln.ln1_w); a.ln_b = P16(Ln.ln1_b); a.ln_out = h; a.ln_eps = 1e-6f;
+      a.ln_counters = ln_counters; a.ln_epoch = ++ln_epoch;
+    }
     if (int rc = gemm_bf16(a, stream)) return rc;
   }
 

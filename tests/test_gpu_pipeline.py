@@ -63,6 +63,23 @@ def test_vit_tokens_and_each_block_vs_oracle(engine2, sd2):
     assert torch.equal(engine2.forward(imgs[4:5].to(dev), layer=2, feature_type="all")[0], allt[4])  # batch invariance
 
 
+@pytest.mark.gpu
+def test_layernorm_fused_into_residual_gemms_is_bit_identical(lib, sd2, monkeypatch):
+    """FP_FUSE_LN (gemm.cu: layernorm_warps; off by default): the next block's norm1 inside fc2 (bit 0) and norm2 inside
+    proj (bit 1) read the rows back through the completion counters and must return the very same tokens as the
+    standalone LayerNorm launches -- at a batch that uses the 2-CTA kernels (>= 2048 token rows), repeatedly."""
+    from freepose_b200.vit_engine import ViTEngine
+    eng = ViTEngine(sd2, chunk=16)
+    torch.manual_seed(5)
+    x = torch.rand(10, 3, 224, 224, device=dev)          # 2 610 token rows in one call
+    monkeypatch.setenv("FP_FUSE_LN", "0")
+    ref = eng.forward(x, layer=2, feature_type="all").clone()
+    for rep in range(6):
+        monkeypatch.setenv("FP_FUSE_LN", str(1 + rep % 3))
+        got = eng.forward(x, layer=2, feature_type="all")
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16)), rep
+
+
 def test_vit_reference_native_420_crops(engine2, sd2):
     """The reference's own crop size (dino_inference.py: 420^2 -> 900 patches + 5 = 905 tokens): interpolated pos-embed,
     the tiled-key attention kernel, and ragged GEMM rows (2 x 905)."""
