@@ -221,6 +221,20 @@ def test_score_bit_exact(ops, B, P):
     assert (ref != want).mean() <= 0.05
 
 
+@pytest.mark.parametrize("D", [256, 512, 768])
+def test_score_bit_exact_other_token_widths(ops, D):
+    """score_rows_kernel is instantiated per D / 256 (ViT-S/B/L widths); 6 hypotheses = one full work item + a tail of two."""
+    from oracle import score as S
+    g = torch.Generator().manual_seed(D)
+    fq = torch.randn(1, 37, D, generator=g).to(bf)
+    ft = (0.6 * fq.float() + 0.8 * torch.randn(6, 37, D, generator=g)).to(bf)
+    scores, idx, vals, patch = ops.score_topk(ft.to(dev), fq.to(dev), k=2, return_patch_scores=True)
+    want, want_patch = S.engine_order_scores(ft, fq, return_patch=True)
+    assert np.array_equal(patch.cpu().numpy(), want_patch) and np.array_equal(scores.cpu().numpy(), want)
+    widx, _ = S.stable_topk(want, 2)
+    assert idx.cpu().numpy().astype(np.int64).tolist() == widx.tolist()
+
+
 def test_score_golden_ties_weights_and_raw_query(ops, golden):
     from oracle import score as S
     g = golden["score"]
