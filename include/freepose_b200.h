@@ -121,6 +121,9 @@ FP_API int fp_normalize_image(const float* image, void* out_bf16, int batch, int
  * feats_t (B,P,D) bf16 template tokens, feat_q (P,D) bf16 query tokens, weights (B,P) fp32 or NULL.
  * scores_out (B) fp32: bf16-rounded mean as float (weights NULL) or the fp32 weighted mean.
  * patch_scores_out (B,P) fp32 or NULL.  top-k: descending, ties -> lowest index.
+ * Three or four launches on `stream`: query normalisation, per-patch cosines (every template token row is read once),
+ * per-hypothesis reduction, top-k.  The workspace holds the normalised query, the top-k scratch and the (B,P) fp32
+ * per-patch cosines (when patch_scores_out is NULL); feats_t must be 16-byte aligned, B * P < 2^31.
  * ------------------------------------------------------------------------------------------------ */
 FP_API size_t fp_score_workspace_bytes(int B, int P, int D);
 FP_API int fp_score_topk(const void* feats_t, const void* feat_q, const float* weights, int B, int P, int D,
