@@ -235,6 +235,30 @@ def test_score_bit_exact_other_token_widths(ops, D):
     assert idx.cpu().numpy().astype(np.int64).tolist() == widx.tolist()
 
 
+def test_score_publish_and_topk_after_exchange_single_rank(ops, tmp_path):
+    """The peer-memory exchange (fp_score_publish / fp_topk_after_exchange) with a world of one:
+    the rank's own buffer is its only peer, so the publishing stores, the completion flag, the epoch parity and the
+    device-side wait all run on a single GPU and must reproduce fp_score_topk bit for bit, exchange after exchange."""
+    import torch.distributed as dist
+    from freepose_b200.distributed import PeerScoreGather
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/rdzv", rank=0, world_size=1)
+    try:
+        B, P = 13, 256
+        sg = PeerScoreGather(B, 1, torch.device(dev), rank=0)
+        for rep in range(5):                                   # five epochs: both parities of the buffer, flags re-armed
+            ft, fq = _score_case(B, P, 77 + rep)
+            want_scores, want_idx, want_val, _ = ops.score_topk(ft.to(dev), fq.to(dev), k=3)
+            sg.score_into(0, ft.to(dev), fq.to(dev))
+            scores, idx, val = sg.gather_topk(0, 3)
+            assert torch.equal(scores, want_scores) and torch.equal(idx, want_idx) and torch.equal(val, want_val), rep
+        sg.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_score_golden_ties_weights_and_raw_query(ops, golden):
     from oracle import score as S
     g = golden["score"]
