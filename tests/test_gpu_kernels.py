@@ -259,6 +259,25 @@ def test_score_publish_and_topk_after_exchange_single_rank(ops, tmp_path):
             dist.destroy_process_group()
 
 
+def test_score_and_vit_edge_cases(ops, lib):
+    """Empty and degenerate inputs at the C boundary: zero hypotheses are a no-op, k larger than the number of hypotheses
+    and a token width the row kernels are not instantiated for are rejected with a message (no launch), a single
+    hypothesis with a single patch works (the smallest work item)."""
+    from freepose_b200 import _lib
+    f = torch.zeros(0, 16, 256, dtype=bf, device=dev)
+    q = torch.randn(16, 256, device=dev).to(bf)
+    scores, idx, vals, _ = ops.score_topk(f, q, k=0)
+    assert scores.numel() == 0
+    with pytest.raises(RuntimeError, match="k=3 out of range"):
+        ops.score_topk(torch.randn(2, 16, 256, device=dev).to(bf), q, k=3)
+    with pytest.raises(RuntimeError, match="multiple of 256"):
+        ops.score_topk(torch.randn(2, 16, 320, device=dev).to(bf), torch.randn(16, 320, device=dev).to(bf), k=1)
+    one = torch.randn(1, 1, 1024, device=dev).to(bf)
+    s1, i1, v1, _ = ops.score_topk(one, one[0], k=1)
+    assert int(i1[0]) == 0 and abs(float(s1[0]) - 1.0) < 2 ** -7          # cosine of a row with itself, bf16-rounded
+    assert _lib.load().fp_last_error() is not None
+
+
 def test_score_golden_ties_weights_and_raw_query(ops, golden):
     from oracle import score as S
     g = golden["score"]
