@@ -665,15 +665,29 @@ __device__ __forceinline__ void shade(const ScreenVertex* __restrict__ svb, cons
   long long area = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
   if (area < 0) { ScreenVertex tmp = v1; v1 = v2; v2 = tmp; int ti = c1; c1 = c2; c2 = ti; area = -area; }
   // perspective weights at (sx, sy) (unbiased edge values: the point may lie outside the triangle)
+  // Triangles whose vertices are < 64 px apart (all but a handful): the shading point lies within a pixel of the
+  // triangle (one of its samples is covered), every coordinate difference is < 2^14 + 2^9 sub-pixels and every edge value
+  // < 2^30: 32-bit integers give exactly the values of the 64-bit form, at a third of the instructions.
+  const bool small = !hard &&
+                     max(v0.x, max(v1.x, v2.x)) - min(v0.x, min(v1.x, v2.x)) < (64 << SUB) &&
+                     max(v0.y, max(v1.y, v2.y)) - min(v0.y, min(v1.y, v2.y)) < (64 << SUB);
   auto weights = [&](long long sx, long long sy, float& w0, float& w1, float& w2, float& wsum) {
-    const long long e0 = (long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x);
-    const long long e1 = (long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x);
-    const long long e2 = (long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x);
+    float f0, f1, f2;
+    if (small) {
+      const int x = int(sx), y = int(sy);
+      f0 = __int2float_rn((v2.x - v1.x) * (y - v1.y) - (v2.y - v1.y) * (x - v1.x));
+      f1 = __int2float_rn((v0.x - v2.x) * (y - v2.y) - (v0.y - v2.y) * (x - v2.x));
+      f2 = __int2float_rn((v1.x - v0.x) * (y - v0.y) - (v1.y - v0.y) * (x - v0.x));
+    } else {
+      f0 = __ll2float_rn((long long)(v2.x - v1.x) * (sy - v1.y) - (long long)(v2.y - v1.y) * (sx - v1.x));
+      f1 = __ll2float_rn((long long)(v0.x - v2.x) * (sy - v2.y) - (long long)(v0.y - v2.y) * (sx - v2.x));
+      f2 = __ll2float_rn((long long)(v1.x - v0.x) * (sy - v0.y) - (long long)(v1.y - v0.y) * (sx - v0.x));
+    }
     // w_i = e_i / z_i (the common factor 1 / area cancels in the ratio below); `wsum` returns 1 / sum w_i: ONE division
     // per evaluation point instead of three for the weights and one per interpolated attribute
-    w0 = __fmul_rn(__ll2float_rn(e0), v0.iz);
-    w1 = __fmul_rn(__ll2float_rn(e1), v1.iz);
-    w2 = __fmul_rn(__ll2float_rn(e2), v2.iz);
+    w0 = __fmul_rn(f0, v0.iz);
+    w1 = __fmul_rn(f1, v1.iz);
+    w2 = __fmul_rn(f2, v2.iz);
     wsum = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(w0, w1), w2));
   };
   auto interp = [&](float w0, float w1, float w2, float rsum, float a0, float a1, float a2) {
