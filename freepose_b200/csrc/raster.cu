@@ -322,16 +322,22 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
       c[i] = int(t.A[i] * ox + t.Bc[i] * oy + t.C[i]);
       bi[i] = int(bias[i]);
     }
+    // incremental form of e_i(pixel, sample) = a_i dx + b_i dy + c_i: the sample offsets are constants, so every sample
+    // is the pixel-origin value plus a per-triangle delta (3 adds instead of 6 multiply-adds; the same integers)
+    int ds[3][S];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int s = 0; s < S; ++s) ds[i][s] = a[i] * c_sample_off[S == 4][s][0] + b[i] * c_sample_off[S == 4][s][1];
     for (int py = t.ymin; py <= t.ymax; ++py) {
       const int dy0 = (py - t.ymin) << SUB;
-      for (int px = t.xmin; px <= t.xmax; ++px) {
-        const int dx0 = (px - t.xmin) << SUB;
+      int o0 = b[0] * dy0 + c[0], o1 = b[1] * dy0 + c[1], o2 = b[2] * dy0 + c[2];   // pixel origin of the row's first pixel
+      for (int px = t.xmin; px <= t.xmax; ++px, o0 += a[0] << SUB, o1 += a[1] << SUB, o2 += a[2] << SUB) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          const int dx = dx0 + c_sample_off[S == 4][s][0], dy = dy0 + c_sample_off[S == 4][s][1];
-          const int e0 = a[0] * dx + b[0] * dy + c[0];
-          const int e1 = a[1] * dx + b[1] * dy + c[1];
-          const int e2 = a[2] * dx + b[2] * dy + c[2];
+          const int e0 = o0 + ds[0][s];
+          const int e1 = o1 + ds[1][s];
+          const int e2 = o2 + ds[2][s];
           if ((e0 | e1 | e2) >= 0) {
             const float f0 = __int2float_rn(e0 + bi[0]), f1 = __int2float_rn(e1 + bi[1]), f2 = __int2float_rn(e2 + bi[2]);
             const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, t.iz[0]), __fmul_rn(f1, t.iz[1])), __fmul_rn(f2, t.iz[2]));
