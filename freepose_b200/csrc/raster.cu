@@ -293,7 +293,69 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   long long bias[3] = {0, 0, 0};
   if (f < F) {
     const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-    if (setup_triangle(svb[i0], svb[i1], svb[i2], res, cull, t)) {
+    ScreenVertex v0 = svb[i0], v1 = svb[i1], v2 = svb[i2];
+    const bool projects = v0.x != INT_MIN && v1.x != INT_MIN && v2.x != INT_MIN;   // (else: hard_triangle_kernel's business)
+    const int minx = min(v0.x, min(v1.x, v2.x)), maxx = max(v0.x, max(v1.x, v2.x));
+    const int miny = min(v0.y, min(v1.y, v2.y)), maxy = max(v0.y, max(v1.y, v2.y));
+    const bool fits32 = projects && (maxx - minx) < (64 << SUB) && (maxy - miny) < (64 << SUB);
+    const int xmin = max(0, minx >> SUB), xmax = min(res - 1, maxx >> SUB);
+    const int ymin = max(0, miny >> SUB), ymax = min(res - 1, maxy >> SUB);
+    const bool on_screen = xmin <= xmax && ymin <= ymax;
+    if (fits32 && on_screen && (xmax - xmin + 1) * (ymax - ymin + 1) <= big_pixels) {
+      // ---- FAST PATH (the common case: ~1 px of area).  With vertices less than 64 px apart every quantity of the set-up
+      // and every edge value relative to the box origin is bounded by 2 * 2^14 * (2^14 + 2^8) < 2^31: the whole triangle
+      // runs in 32-bit integers -- exactly the values of the 64-bit form (setup_triangle / raster_pixel / the oracle) --
+      // and never builds the 64-bit TriSetup.
+      int area = (v1.x - v0.x) * (v2.y - v0.y) - (v2.x - v0.x) * (v1.y - v0.y);
+      // image coordinates have y down: GL-front-facing (CCW in the y-up window) <=> area < 0 here
+      if (area != 0 && !(cull && area > 0)) {
+        if (area < 0) { const ScreenVertex tmp = v1; v1 = v2; v2 = tmp; area = -area; }
+        const float farea = __int2float_rn(area);
+        const int ox = xmin << SUB, oy = ymin << SUB;
+        const ScreenVertex* ea[3] = {&v1, &v2, &v0};   // edge i runs ea[i] -> eb[i]; weight i belongs to vertex i
+        const ScreenVertex* eb[3] = {&v2, &v0, &v1};
+        int ax[3], o_row[3], bi[3], by[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int dx = eb[i]->x - ea[i]->x, dy = eb[i]->y - ea[i]->y;
+          const bool topleft = (dy < 0) || (dy == 0 && dx > 0);
+          bi[i] = topleft ? 0 : 1;                      // "E >= 0" implements the top-left rule with the bias folded in
+          ax[i] = -dy;
+          by[i] = dx;
+          o_row[i] = dx * (oy - ea[i]->y) - dy * (ox - ea[i]->x) - bi[i];   // value at the box origin
+        }
+        const float iz0 = v0.iz, iz1 = v1.iz, iz2 = v2.iz;
+        // e_i(pixel, sample) = origin value + a_i dx + b_i dy: the sample offsets are constants, so every sample is the
+        // pixel-origin value plus a per-triangle delta (3 adds instead of 6 multiply-adds; the same integers)
+        int ds[3][S];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int s = 0; s < S; ++s) ds[i][s] = ax[i] * c_sample_off[S == 4][s][0] + by[i] * c_sample_off[S == 4][s][1];
+        for (int py = ymin; py <= ymax; ++py) {
+          int o0 = o_row[0], o1 = o_row[1], o2 = o_row[2];
+          for (int px = xmin; px <= xmax; ++px, o0 += ax[0] << SUB, o1 += ax[1] << SUB, o2 += ax[2] << SUB) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int e0 = o0 + ds[0][s];
+              const int e1 = o1 + ds[1][s];
+              const int e2 = o2 + ds[2][s];
+              if ((e0 | e1 | e2) >= 0) {
+                const float f0 = __int2float_rn(e0 + bi[0]), f1 = __int2float_rn(e1 + bi[1]), f2 = __int2float_rn(e2 + bi[2]);
+                const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, iz0), __fmul_rn(f1, iz1)), __fmul_rn(f2, iz2));
+                const float z = __fdiv_rn(farea, den);   // (sample_depth's expression)
+                if (z > ZNEAR && z < ZFAR)
+                  atomicMin(&keys_view[(size_t(py) * res + px) * S + s],
+                            ((unsigned long long)__float_as_uint(z) << 32) | unsigned(f));
+              }
+            }
+          }
+          o_row[0] += by[0] << SUB; o_row[1] += by[1] << SUB; o_row[2] += by[2] << SUB;
+        }
+      }
+    } else if (projects && on_screen && setup_triangle(v0, v1, v2, res, cull, t)) {
+      // ---- everything else keeps the 64-bit set-up: large triangles (warp-cooperative walk below) and triangles that are
+      // small on screen but long off screen (clipped by the viewport)
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const long long dx = t.Bc[i], dy = -t.A[i];
@@ -304,51 +366,10 @@ triangle_kernel(const ScreenVertex* __restrict__ sv, const int* __restrict__ fac
   const int w = t.valid ? (t.xmax - t.xmin + 1) : 0;
   const int h = t.valid ? (t.ymax - t.ymin + 1) : 0;
   const bool big = w * h > big_pixels;
-  if (t.valid && !big && !t.fits32) {
+  if (t.valid && !big) {
     // small on screen but long off screen (clipped by the viewport): 64-bit evaluation per sample
     for (int py = t.ymin; py <= t.ymax; ++py)
       for (int px = t.xmin; px <= t.xmax; ++px) raster_pixel<S>(t, bias, px, py, keys_view, res, unsigned(f), ZNEAR, ZFAR);
-  }
-  if (t.valid && !big && t.fits32) {
-    // Small triangles (the common case: ~1 px of area): with vertices less than 64 px apart, every edge-function value
-    // relative to the box origin is bounded by 2 * 2^14 * (2^14 + 2^8) < 2^31, so the per-sample evaluation runs in 32-bit
-    // integers -- exactly the values of the 64-bit form in raster_pixel / the oracle, at a third of the instructions
-    // (2.92 -> 2.19 ms per 521 views).
-    const long long ox = (long long)t.xmin << SUB, oy = (long long)t.ymin << SUB;
-    int a[3], b[3], c[3], bi[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      a[i] = int(t.A[i]); b[i] = int(t.Bc[i]);
-      c[i] = int(t.A[i] * ox + t.Bc[i] * oy + t.C[i]);
-      bi[i] = int(bias[i]);
-    }
-    // incremental form of e_i(pixel, sample) = a_i dx + b_i dy + c_i: the sample offsets are constants, so every sample
-    // is the pixel-origin value plus a per-triangle delta (3 adds instead of 6 multiply-adds; the same integers)
-    int ds[3][S];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int s = 0; s < S; ++s) ds[i][s] = a[i] * c_sample_off[S == 4][s][0] + b[i] * c_sample_off[S == 4][s][1];
-    for (int py = t.ymin; py <= t.ymax; ++py) {
-      const int dy0 = (py - t.ymin) << SUB;
-      int o0 = b[0] * dy0 + c[0], o1 = b[1] * dy0 + c[1], o2 = b[2] * dy0 + c[2];   // pixel origin of the row's first pixel
-      for (int px = t.xmin; px <= t.xmax; ++px, o0 += a[0] << SUB, o1 += a[1] << SUB, o2 += a[2] << SUB) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const int e0 = o0 + ds[0][s];
-          const int e1 = o1 + ds[1][s];
-          const int e2 = o2 + ds[2][s];
-          if ((e0 | e1 | e2) >= 0) {
-            const float f0 = __int2float_rn(e0 + bi[0]), f1 = __int2float_rn(e1 + bi[1]), f2 = __int2float_rn(e2 + bi[2]);
-            const float den = __fadd_rn(__fadd_rn(__fmul_rn(f0, t.iz[0]), __fmul_rn(f1, t.iz[1])), __fmul_rn(f2, t.iz[2]));
-            const float z = __fdiv_rn(t.area, den);   // (sample_depth's expression)
-            if (z > ZNEAR && z < ZFAR)
-              atomicMin(&keys_view[(size_t(py) * res + px) * S + s],
-                        ((unsigned long long)__float_as_uint(z) << 32) | unsigned(f));
-          }
-        }
-      }
-    }
   }
   // large triangles: the whole warp walks the bounding box of one triangle at a time
   unsigned todo = __ballot_sync(0xffffffffu, big);
