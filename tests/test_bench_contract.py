@@ -45,7 +45,8 @@ def test_b200_arm_json_line():
 def test_b200_arm_parity_block_and_cpu_baseline():
     """The same-run parity gates of SURVEY.md section 8d (small sample so the test stays short)."""
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "3", "--hyp", "16",
-                        "--chunk", "17", "--layer", "2", "--ref-hyp", "4"], capture_output=True, text=True,
+                        "--chunk", "17", "--layer", "2", "--ref-hyp", "4", "--cpu-hyp", "4", "--cpu-samples", "2"],
+                       capture_output=True, text=True,
                        timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
