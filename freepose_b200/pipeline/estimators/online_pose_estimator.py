@@ -100,13 +100,13 @@ class DinoOnlinePoseEstimator(nn.Module):
             # frames > 0: the query crop rides in the same batch as the ~19 fine renders (one ViT forward instead of two;
             # the reference runs it as a separate batch of one, online_pose_estimator.py:50-52 -- same arithmetic per image)
             patches = torch.empty((B + 1) * P, ops.KPAD, dtype=torch.bfloat16, device=self.device)
-            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches)
+            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches, want_mask=mask_scores)
             q = torch.as_tensor(proposal).to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
             ops.im2col(q[None], out=patches[B * P:])
             both = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
             feats, query_feat = both[:B], both[B:]
         else:
-            patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True)
+            patches, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, want_mask=mask_scores)
             feats = self.feature_extractor.forward_patches(patches, res=T, layer=layer)
         weights = None
         if mask_scores:
@@ -157,7 +157,8 @@ class DinoOnlinePoseEstimator(nn.Module):
         for pl in plans:
             B = len(pl["close"])
             rgb, depth = self.renderer.render_device(self._scaled_mesh(pl["it"]["mesh"]), pl["selected"])
-            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches[row * P:])
+            _, _, masks, _ = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches[row * P:],
+                                                            want_mask=mask_scores)
             pl.update(depth=depth, masks=masks, lo=row, hi=row + B)
             row += B
             if pl["query_feat"] is None:

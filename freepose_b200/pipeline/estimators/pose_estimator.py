@@ -166,7 +166,7 @@ class DinoPoseEstimator(nn.Module):
         B, P = rgb.shape[0], (T // 14) ** 2
         n_img = B + (1 if query is not None else 0)
         patches = torch.empty(n_img * P, ops.KPAD, dtype=bf16, device=self.device)
-        _, _, _, status = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches)
+        _, _, _, status = self.renderer.proposals_device(rgb, depth, T, to_patches=True, out=patches, want_mask=False)
         if query is not None:
             q = query.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
             ops.im2col(q[None], out=patches[B * P:])

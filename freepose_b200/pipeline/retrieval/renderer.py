@@ -51,13 +51,14 @@ class MeshRenderer:
         return torch.as_tensor(np.asarray(poses), dtype=torch.float32).to(self.device, non_blocking=True)
 
     @on_device
-    def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None):
+    def proposals_device(self, rgb, depth, resolution=None, to_patches=True, out=None, want_mask=True):
         """Device version of generate_proposals: mask -> bbox -> CropResizePad.  Returns
-        (patch matrix | fp32 crops, bbox (B,4) int32, masks u8 (B,res,res))."""
+        (patch matrix | fp32 crops, bbox (B,4) int32, masks u8 (B,res,res) | None, status).  ``want_mask=False`` skips
+        writing the masks (a second pass over the depth maps) for callers that only need the crops."""
         res = rgb.shape[1]
         T = resolution or res
         lo, hi = (105, 315) if res == 420 else (res // 4, res - res // 4)  # renderer.py:117 is hard-coded for 420
-        bbox, count, mask = ops.mask_bbox(depth, fallback=(lo, hi), min_count=100, return_mask=True)
+        bbox, count, mask = ops.mask_bbox(depth, fallback=(lo, hi), min_count=100, return_mask=want_mask)
         out, status = ops.crop_resize_pad(rgb, bbox, T, to_patches=to_patches, out=out)
         return out, bbox, mask, status
 
